@@ -1,0 +1,114 @@
+// extern "C" surface of libdcvit.so (declared in include/dcvit.h) plus the host
+// utilities shared by all launchers.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "host.h"
+
+namespace dcv {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_bytes & 15))
+    return set_error(DCV_ERR_UNSUPPORTED, "TMA operand must be 16-byte aligned (ptr %p, row stride %llu)", ptr,
+                     (unsigned long long)row_stride_bytes);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(2d %llux%llu box %ux%u) failed: %d",
+                     (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer, (int)r);
+  return 0;
+}
+
+int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15))
+    return set_error(DCV_ERR_UNSUPPORTED, "TMA operand must be 16-byte aligned");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return 0;
+}
+
+}  // namespace dcv
+
+using namespace dcv;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* dcv_last_error(void) { return g_err; }
+int dcv_version(void) { return 1; }
+long long dcv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dcv_gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue,
+                const float* bias, void* out, void* out2, const float* resid, const void* aux, int ldo,
+                void* stream) {
+  if (!A || !B) return set_error(DCV_ERR_INVALID, "dcv_gemm_nt: null operand");
+  return gemm_nt(A, lda, B, ldb, M, N, K, epilogue, bias, out, out2, resid, aux, ldo, ST(stream));
+}
+
+int dcv_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
+                int accumulate, int splits, void* stream) {
+  if (!A || !B || !C) return set_error(DCV_ERR_INVALID, "dcv_gemm_tn: null operand");
+  return gemm_tn(A, lda, B, ldb, M, Nout, Kout, C, ldc, accumulate, splits, ST(stream));
+}
+
+void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo_bytes, sbo_bytes); }
+
+}  // extern "C"

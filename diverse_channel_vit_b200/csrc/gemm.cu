@@ -1,0 +1,504 @@
+// tcgen05 GEMM family for the transformer blocks of the DiChaViT hot path.
+//
+//   gemm_nt :  C[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)        -- both operands K-major
+//              forward Linear layers (reference models/vit.py:116,118,71-73) and their
+//              dgrad (dX = dY * W, run against a pre-transposed bf16 copy of W).
+//   gemm_tn :  C[N,K] += A[M,N]^T * B[M,K]                             -- both operands MN-major
+//              weight gradients dW = dY^T X, reduction over the B*L token rows, split-K.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B boxes, kStages-deep ring)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma, fp32 accumulators in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       (tcgen05.ld -> registers -> bias/GELU/residual -> global)
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#include "common.cuh"
+#include "host.h"
+
+namespace dcv {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // one 128-byte swizzle atom of bf16
+
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,        // out_bf16 = acc (+ bias)
+  EPI_BIAS_GELU = 1,   // out_bf16 = h = acc + bias ; out2_bf16 = gelu(h)
+  EPI_BIAS_RESID = 2,  // out_f32 = resid + acc + bias   (resid may alias out_f32)
+  EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux)
+  EPI_F32 = 4,         // out_f32 = acc (+ bias)
+};
+
+struct GemmNtParams {
+  int M, N, K;
+  int ldo;  // leading dimension (elements) of out / out2 / resid / aux
+  const float* bias;
+  __nv_bfloat16* out_bf16;
+  __nv_bfloat16* out2_bf16;
+  float* out_f32;
+  const float* resid;
+  const __nv_bfloat16* aux;
+};
+
+template <int BN>
+struct NtCfg {
+  static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
+  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const GemmNtParams p) {
+  using Cfg = NtCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                              // kStages x [128][64] bf16
+  uint8_t* smem_b = smem + kStages * (kBM * kBK * 2);  // kStages x [BN][64] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = p.N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * (kBM * kBK * 2), &map_a, &full_bar[stage], kb * kBK, m0);
+          tma_load_2d(smem_b + stage * (BN * kBK * 2), &map_b, &full_bar[stage], kb * kBK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_desc_kmajor(smem_u32(smem_a + stage * (kBM * kBK * 2)));
+          const uint64_t db = make_desc_kmajor(smem_u32(smem_b + stage * (BN * kBK * 2)));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes per 16-element K step inside the swizzle atom (encoded >> 4)
+            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------- epilogue --------------------------------
+    const int q = warp & 3;  // TMEM lane quadrant owned by this warp
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kBM;
+      const int n0 = (tile % n_tiles) * BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const size_t row_off = static_cast<size_t>(row) * p.ldo;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (EPI != EPI_DGELU && p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+        if (row_ok) {
+          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + row_off + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+              o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+              o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+              o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+              dst[i] = o;
+            }
+            if (EPI == EPI_BIAS_GELU) {
+              uint4* dst2 = reinterpret_cast<uint4*>(p.out2_bf16 + row_off + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 o;
+                o.x = pack_bf16(gelu_exact(v[8 * i + 0]), gelu_exact(v[8 * i + 1]));
+                o.y = pack_bf16(gelu_exact(v[8 * i + 2]), gelu_exact(v[8 * i + 3]));
+                o.z = pack_bf16(gelu_exact(v[8 * i + 4]), gelu_exact(v[8 * i + 5]));
+                o.w = pack_bf16(gelu_exact(v[8 * i + 6]), gelu_exact(v[8 * i + 7]));
+                dst2[i] = o;
+              }
+            }
+          } else if (EPI == EPI_DGELU) {
+            const uint4* hsrc = reinterpret_cast<const uint4*>(p.aux + row_off + col0);
+            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + row_off + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 h4 = __ldg(hsrc + i);
+              const float2 h0 = unpack_bf16(h4.x), h1 = unpack_bf16(h4.y), h2 = unpack_bf16(h4.z),
+                           h3 = unpack_bf16(h4.w);
+              uint4 o;
+              o.x = pack_bf16(v[8 * i + 0] * gelu_exact_grad(h0.x), v[8 * i + 1] * gelu_exact_grad(h0.y));
+              o.y = pack_bf16(v[8 * i + 2] * gelu_exact_grad(h1.x), v[8 * i + 3] * gelu_exact_grad(h1.y));
+              o.z = pack_bf16(v[8 * i + 4] * gelu_exact_grad(h2.x), v[8 * i + 5] * gelu_exact_grad(h2.y));
+              o.w = pack_bf16(v[8 * i + 6] * gelu_exact_grad(h3.x), v[8 * i + 7] * gelu_exact_grad(h3.y));
+              dst[i] = o;
+            }
+          } else {  // EPI_BIAS_RESID / EPI_F32
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + row_off + col0);
+            if (EPI == EPI_BIAS_RESID) {
+              const float4* rs = reinterpret_cast<const float4*>(p.resid + row_off + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 r4 = rs[i];
+                v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// gemm_tn: C[Nout, Kout] (+)= sum_m A[m, Nout]^T * B[m, Kout]
+// One CTA per (128 x BN output tile, split of the M reduction).
+// ---------------------------------------------------------------------------
+struct GemmTnParams {
+  int M, Nout, Kout;
+  int ldc;
+  int splits;
+  int use_atomic;  // 1: atomicAdd into C (C pre-initialised), 0: plain store (splits must be 1)
+  float* C;
+  uint32_t lbo_a, lbo_b, sbo;  // descriptor strides (debug-overridable)
+};
+
+template <int BN>
+struct TnCfg {
+  static constexpr int kABytes = kBM * kBK * 2;  // 2 MN chunks of [64 m-rows][64] bf16
+  static constexpr int kBBytes = BN * kBK * 2;   // BN/64 chunks
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kTmemCols = (BN <= 128) ? 128 : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const GemmTnParams p) {
+  using Cfg = TnCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int k_tiles = p.Kout / BN;
+  const int n_tiles = (p.Nout + kBM - 1) / kBM;
+  const int tile = blockIdx.x % (k_tiles * n_tiles);
+  const int split = blockIdx.x / (k_tiles * n_tiles);
+  const int n0 = (tile / k_tiles) * kBM;  // rows of C
+  const int k0 = (tile % k_tiles) * BN;   // cols of C
+  const int total_mb = (p.M + kBK - 1) / kBK;
+  const int mb_per = (total_mb + p.splits - 1) / p.splits;
+  const int mb_begin = split * mb_per;
+  const int mb_end = min(total_mb, mb_begin + mb_per);
+  const int num_mb = max(0, mb_end - mb_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (num_mb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mb = mb_begin; mb < mb_end; ++mb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem_a + stage * Cfg::kABytes;
+          uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+#pragma unroll
+          for (int c = 0; c < kBM / 64; ++c)
+            tma_load_2d(sa + c * (64 * 128), &map_a, &full_bar[stage], n0 + c * 64, mb * kBK);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sb + c * (64 * 128), &map_b, &full_bar[stage], k0 + c * 64, mb * kBK);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mb = 0; mb < num_mb; ++mb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes), p.lbo_a, p.sbo);
+          const uint64_t db = make_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), p.lbo_b, p.sbo);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // 16 reduction rows = 2 swizzle atoms = 2048 bytes (encoded >> 4 = 128)
+            umma_ss(tmem_base, da + 128 * k, db + 128 * k, idesc, (mb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full);
+      }
+    } else if (warp >= 4) {
+      const int q = warp & 3;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int row = n0 + q * 32 + lane;
+      const bool row_ok = row < p.Nout;
+      float* crow = p.C + static_cast<size_t>(row) * p.ldc + k0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          if (p.use_atomic) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(crow + c * 32 + i, __uint_as_float(r[i]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+static int g_tn_lbo = 0, g_tn_sbo = 0;  // debug overrides (0 = default)
+
+template <int BN, int EPI>
+static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p, cudaStream_t st) {
+  using Cfg = NtCfg<BN>;
+  auto kern = gemm_nt_kernel<BN, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 256, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <int BN>
+static int dispatch_nt_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p,
+                           cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS: return launch_nt<BN, EPI_BIAS>(ma, mb, p, st);
+    case EPI_BIAS_GELU: return launch_nt<BN, EPI_BIAS_GELU>(ma, mb, p, st);
+    case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID>(ma, mb, p, st);
+    case EPI_DGELU: return launch_nt<BN, EPI_DGELU>(ma, mb, p, st);
+    case EPI_F32: return launch_nt<BN, EPI_F32>(ma, mb, p, st);
+  }
+  return set_error(DCV_ERR_INVALID, "gemm_nt: unknown epilogue %d", epi);
+}
+
+int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
+            void* out, void* out2, const float* resid, const void* aux, int ldo, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(DCV_ERR_INVALID, "gemm_nt: empty problem %dx%dx%d", M, N, K);
+  if (K % 8 || lda % 8 || ldb % 8 || ldo % 8)
+    return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: K/lda/ldb/ldo must be multiples of 8 (16-byte rows)");
+  int bn = 0;
+  if (N % 192 == 0) bn = 192;
+  else if (N % 128 == 0) bn = 128;
+  else if (N % 64 == 0) bn = 64;
+  else return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: N=%d must be a multiple of 64", N);
+  CUtensorMap ma, mb;
+  if (int e = make_tmap_bf16_2d(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM)) return e;
+  if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, bn)) return e;
+  GemmNtParams p;
+  p.M = M; p.N = N; p.K = K; p.ldo = ldo; p.bias = bias;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(out2);
+  p.out_f32 = reinterpret_cast<float*>(out);
+  p.resid = resid;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
+  if ((epi == EPI_BIAS_GELU && !out2) || (epi == EPI_BIAS_RESID && !resid) || (epi == EPI_DGELU && !aux) || !out)
+    return set_error(DCV_ERR_INVALID, "gemm_nt: missing buffer for epilogue %d", epi);
+  switch (bn) {
+    case 192: return dispatch_nt_epi<192>(epi, ma, mb, p, st);
+    case 128: return dispatch_nt_epi<128>(epi, ma, mb, p, st);
+    default: return dispatch_nt_epi<64>(epi, ma, mb, p, st);
+  }
+}
+
+template <int BN>
+static int launch_tn(const CUtensorMap& ma, const CUtensorMap& mb, GemmTnParams p, cudaStream_t st) {
+  using Cfg = TnCfg<BN>;
+  auto kern = gemm_tn_kernel<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = ((p.Nout + kBM - 1) / kBM) * (p.Kout / BN);
+  const int total_mb = (p.M + kBK - 1) / kBK;
+  int splits = p.splits;
+  if (splits <= 0) {  // fill the machine once
+    splits = num_sms() / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > total_mb) splits = total_mb;
+  }
+  if (!p.use_atomic) splits = 1;
+  p.splits = splits;
+  p.lbo_a = g_tn_lbo ? g_tn_lbo : 64 * 128;
+  p.lbo_b = g_tn_lbo ? g_tn_lbo : 64 * 128;
+  p.sbo = g_tn_sbo ? g_tn_sbo : 1024;
+  kern<<<tiles * splits, 256, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
+            int accumulate, int splits, cudaStream_t st) {
+  if (M <= 0 || Nout <= 0 || Kout <= 0) return set_error(DCV_ERR_INVALID, "gemm_tn: empty problem");
+  if (lda % 8 || ldb % 8 || Nout % 64 || ldc % 4)
+    return set_error(DCV_ERR_UNSUPPORTED, "gemm_tn: lda/ldb %% 8, Nout %% 64, ldc %% 4 required");
+  int bn = 0;
+  if (Kout % 192 == 0) bn = 192;
+  else if (Kout % 128 == 0) bn = 128;
+  else if (Kout % 64 == 0) bn = 64;
+  else return set_error(DCV_ERR_UNSUPPORTED, "gemm_tn: Kout=%d must be a multiple of 64", Kout);
+  CUtensorMap ma, mb;
+  if (int e = make_tmap_bf16_2d(&ma, A, (uint64_t)Nout, (uint64_t)M, (uint64_t)lda * 2, 64, kBK)) return e;
+  if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)Kout, (uint64_t)M, (uint64_t)ldb * 2, 64, kBK)) return e;
+  GemmTnParams p;
+  p.M = M; p.Nout = Nout; p.Kout = Kout; p.ldc = ldc; p.splits = splits; p.use_atomic = accumulate; p.C = C;
+  switch (bn) {
+    case 192: return launch_tn<192>(ma, mb, p, st);
+    case 128: return launch_tn<128>(ma, mb, p, st);
+    default: return launch_tn<64>(ma, mb, p, st);
+  }
+}
+
+void debug_set_tn_desc(int lbo, int sbo) { g_tn_lbo = lbo; g_tn_sbo = sbo; }
+
+}  // namespace dcv

@@ -1,0 +1,55 @@
+"""Thin Python wrappers over the C ABI (include/dcvit.h): shape checks + pointer passing.
+
+Every function enqueues work on the current CUDA stream and returns immediately.
+PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_DGELU, EPI_F32 = 0, 1, 2, 3, 4
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.DcvError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.DcvError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise _lib.DcvError(f"{name}: innermost dimension must be contiguous")
+
+
+def gemm_nt(a, b, epilogue=EPI_BIAS, bias=None, out=None, out2=None, resid=None, aux=None):
+    """out = a[M,K] @ b[N,K]^T with fused epilogue (see dcvit.h DCV_EPI_*)."""
+    _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
+    M, K = a.shape
+    N, K2 = b.shape
+    assert K == K2
+    f32_out = epilogue in (EPI_BIAS_RESID, EPI_F32)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if f32_out else torch.bfloat16)
+    if epilogue == EPI_BIAS_GELU and out2 is None:
+        out2 = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    ldo = out.stride(0)
+    for t in (out2, resid, aux):
+        if t is not None:
+            assert t.stride(0) == ldo
+    check(_lib.lib().dcv_gemm_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, epilogue, ptr(bias), ptr(out),
+                                 ptr(out2), ptr(resid), ptr(aux), ldo, stream_ptr()), "dcv_gemm_nt")
+    return (out, out2) if epilogue == EPI_BIAS_GELU else out
+
+
+def gemm_tn(a, b, out=None, accumulate=True, splits=0):
+    """out[Nout,Kout] (+)= a[M,Nout]^T @ b[M,Kout]; fp32 output."""
+    _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
+    M, Nout = a.shape
+    M2, Kout = b.shape
+    assert M == M2
+    if out is None:
+        out = torch.zeros((Nout, Kout), device=a.device, dtype=torch.float32)
+    check(_lib.lib().dcv_gemm_tn(ptr(a), a.stride(0), ptr(b), b.stride(0), M, Nout, Kout, ptr(out), out.stride(0),
+                                 1 if accumulate else 0, splits, stream_ptr()), "dcv_gemm_tn")
+    return out
