@@ -109,6 +109,11 @@ int dcv_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout,
   return gemm_tn(A, lda, B, ldb, M, Nout, Kout, C, ldc, accumulate, splits, ST(stream));
 }
 
+int dcv_attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, void* stream) {
+  if (!qkv || !o || !lse2) return set_error(DCV_ERR_INVALID, "dcv_attn_fwd: null pointer");
+  return attn_fwd(qkv, o, lse2, B, L, H, scale, ST(stream));
+}
+
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo_bytes, sbo_bytes); }
 
 }  // extern "C"

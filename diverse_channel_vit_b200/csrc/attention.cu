@@ -1,0 +1,250 @@
+// Flash-style multi-head self-attention over the C'*N+1 channel-patch tokens, on
+// tcgen05 tensor cores with TMEM accumulators (head_dim = 64 for every DiChaViT size).
+// Replaces reference models/vit.py:126-141:  softmax(q k^T * hd^-0.5) v, which there
+// materialises the [B,H,L,L] probabilities; here only O and the per-row log-sum-exp
+// are written.
+//
+// Input  qkv  bf16 [B, L, 3*D]   (row = token, columns [q | k | v], head h at h*64)
+// Output o    bf16 [B, L, D]     (head-major columns == reference's transpose(1,2).reshape)
+//        lse2 fp32 [B, H, L]     (log2-domain: max + log2(sum) of scale*log2e-scaled scores)
+//
+// Forward kernel, one CTA per (128-query tile, head, image), 2 CTAs resident per SM:
+//   warps 0-3  softmax warpgroup: thread t owns query row t (TMEM lane t)
+//   warp  4    TMA producer (Q once, K/V tiles through a 2-stage ring)
+//   warp  5    MMA issuer + TMEM owner
+//   TMEM columns: S[0,128) fp32 | P[128,192) bf16x2 (A operand of the PV MMA) | PV[192,256)
+// Per KV tile: S = Q K^T (SS MMA) -> online softmax in registers -> P to TMEM ->
+// PV = P V (TS MMA, V consumed MN-major straight from its TMA tile) -> O = O*alpha + PV.
+#include "common.cuh"
+#include "host.h"
+
+namespace dcv {
+
+constexpr int kHd = 64;
+constexpr int kTq = 128;
+constexpr int kTk = 128;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnFwdParams {
+  int B, L, H, D;
+  float sl2;  // softmax scale * log2(e)
+  __nv_bfloat16* o;
+  float* lse2;
+};
+
+constexpr int kFwdStages = 2;
+constexpr int kFwdSmem = kTq * kHd * 2 + kFwdStages * 2 * kTk * kHd * 2 + 1024 + 128;
+
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTq * kHd * 2;                       // kFwdStages x 16 KB
+  uint8_t* sV = sK + kFwdStages * kTk * kHd * 2;            // kFwdStages x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kFwdStages * kTk * kHd * 2);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = bars + 1 + kFwdStages;
+  uint64_t* s_full = bars + 1 + 2 * kFwdStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_full = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTq;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_kv = (p.L + kTk - 1) / kTk;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_qkv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kFwdStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tP = tmem_base + 128, tPV = tmem_base + 192;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTq * kHd * 2);
+      tma_load_3d(sQ, &map_qkv, q_full, h * kHd, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kFwdStages;
+        mbar_wait(&kv_empty[st], ((j / kFwdStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTk * kHd * 2);
+        tma_load_3d(sK + st * (kTk * kHd * 2), &map_qkv, &kv_full[st], p.D + h * kHd, j * kTk, b);
+        tma_load_3d(sV + st * (kTk * kHd * 2), &map_qkv, &kv_full[st], 2 * p.D + h * kHd, j * kTk, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kTq, kTk, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTq, kHd, 0, 1);  // B = V, MN-major
+      const uint64_t dq = make_desc_kmajor(smem_u32(sQ));
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      {
+        const uint64_t dk = make_desc_kmajor(smem_u32(sK));
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kFwdStages;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint64_t dv = make_desc_mnmajor(smem_u32(sV + st * (kTk * kHd * 2)), 64 * 128);
+#pragma unroll
+        for (int k = 0; k < kTk / 16; ++k) umma_ts(tPV, tP + 8 * k, dv + 128 * k, idesc_pv, k ? 1u : 0u);
+        umma_commit(pv_full);
+        umma_commit(&kv_empty[st]);
+        if (j + 1 < n_kv) {
+          const int st1 = (j + 1) % kFwdStages;
+          mbar_wait(&kv_full[st1], ((j + 1) / kFwdStages) & 1);
+          tc_fence_after();
+          const uint64_t dk = make_desc_kmajor(smem_u32(sK + st1 * (kTk * kHd * 2)));
+#pragma unroll
+          for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax warpgroup ------------------------------
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const int row = q0 + warp * 32 + lane;
+    float m = -INFINITY, l = 0.f;
+    float o[kHd];
+#pragma unroll
+    for (int i = 0; i < kHd; ++i) o[i] = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * kTk;
+      const bool tail = kv0 + kTk > p.L;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kTk / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_base + c * 32, r);
+        tmem_ld_wait();
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + c * 32 + i < p.L) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx * p.sl2);
+      const float alpha = fast_exp2(m - m_new);
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kTk / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_base + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.sl2, -m_new));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -m_new));
+          if (tail) {
+            if (kv0 + c * 32 + 2 * i >= p.L) p0 = 0.f;
+            if (kv0 + c * 32 + 2 * i + 1 >= p.L) p1 = 0.f;
+          }
+          sum += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        tmem_st16(tP + lane_base + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      l = l * alpha + sum;
+      m = m_new;
+
+      mbar_wait(pv_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kHd / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tPV + lane_base + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+    }
+
+    if (row < p.L) {
+      const float inv = 1.0f / l;
+      __nv_bfloat16* dst = p.o + (static_cast<size_t>(b) * p.L + row) * p.D + h * kHd;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < kHd / 8; ++i) {
+        uint4 v;
+        v.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+        v.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+        v.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+        v.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        d4[i] = v;
+      }
+      p.lse2[(static_cast<size_t>(b) * p.H + h) * p.L + row] = m + log2f(l);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st) {
+  if (B <= 0 || L <= 0 || H <= 0) return set_error(DCV_ERR_INVALID, "attn_fwd: empty problem");
+  const int D = H * kHd;
+  CUtensorMap map;
+  if (int e = make_tmap_bf16_3d(&map, qkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D * 2,
+                                (uint64_t)L * 3 * D * 2, kHd, kTq, 1))
+    return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DCV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    attr_done = true;
+  }
+  AttnFwdParams p;
+  p.B = B; p.L = L; p.H = H; p.D = D;
+  p.sl2 = scale * 1.4426950408889634f;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.lse2 = lse2;
+  dim3 grid((L + kTq - 1) / kTq, H, B);
+  attn_fwd_kernel<<<grid, 192, kFwdSmem, st>>>(map, p);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace dcv

@@ -5,6 +5,8 @@ PyTorch is used only for device memory and streams.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -53,3 +55,18 @@ def gemm_tn(a, b, out=None, accumulate=True, splits=0):
     check(_lib.lib().dcv_gemm_tn(ptr(a), a.stride(0), ptr(b), b.stride(0), M, Nout, Kout, ptr(out), out.stride(0),
                                  1 if accumulate else 0, splits, stream_ptr()), "dcv_gemm_tn")
     return out
+
+
+def attn_fwd(qkv, B, L, H, scale=None, o=None, lse2=None):
+    """qkv bf16 [B*L, 3*H*64] -> (o bf16 [B*L, H*64], lse2 fp32 [B,H,L])."""
+    _req(qkv, torch.bfloat16, "qkv")
+    D = H * 64
+    assert qkv.is_contiguous() and qkv.numel() == B * L * 3 * D
+    if o is None:
+        o = torch.empty((B * L, D), device=qkv.device, dtype=torch.bfloat16)
+    if lse2 is None:
+        lse2 = torch.empty((B, H, L), device=qkv.device, dtype=torch.float32)
+    scale = 64 ** -0.5 if scale is None else scale
+    check(_lib.lib().dcv_attn_fwd(ptr(qkv), ptr(o), ptr(lse2), B, L, H, ctypes.c_float(scale), stream_ptr()),
+          "dcv_attn_fwd")
+    return o, lse2

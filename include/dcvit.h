@@ -55,6 +55,12 @@ int dcv_gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, in
 int dcv_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
                 int accumulate, int splits, void* stream);
 
+/* Multi-head self-attention forward, head_dim 64: o = softmax(q k^T * scale) v.
+ * qkv bf16 [B, L, 3*H*64] (columns q|k|v, head h at h*64), o bf16 [B, L, H*64],
+ * lse2 fp32 [B, H, L] = log2-domain log-sum-exp of the scaled scores (saved for backward).
+ * Replaces models/vit.py:123-141 (q @ k^T * scale, softmax, attn @ v, transpose/reshape). */
+int dcv_attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, void* stream);
+
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);
 
