@@ -114,6 +114,13 @@ int dcv_attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, flo
   return attn_fwd(qkv, o, lse2, B, L, H, scale, ST(stream));
 }
 
+int dcv_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
+                 void* dqkv, int B, int L, int H, float scale, void* stream) {
+  if (!qkv || !o || !dO || !lse2 || !delta || !dq_acc || !dqkv)
+    return set_error(DCV_ERR_INVALID, "dcv_attn_bwd: null pointer");
+  return attn_bwd(qkv, o, dO, lse2, delta, dq_acc, dqkv, B, L, H, scale, ST(stream));
+}
+
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo_bytes, sbo_bytes); }
 
 }  // extern "C"

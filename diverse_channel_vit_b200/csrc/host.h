@@ -37,5 +37,7 @@ void debug_set_tn_desc(int lbo, int sbo);
 
 // ---- attention.cu ----
 int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st);
+int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
+             void* dqkv, int B, int L, int H, float scale, cudaStream_t st);
 
 }  // namespace dcv

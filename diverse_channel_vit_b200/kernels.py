@@ -57,6 +57,10 @@ def gemm_tn(a, b, out=None, accumulate=True, splits=0):
     return out
 
 
+def lpad(L: int) -> int:
+    return (L + 127) // 128 * 128
+
+
 def attn_fwd(qkv, B, L, H, scale=None, o=None, lse2=None):
     """qkv bf16 [B*L, 3*H*64] -> (o bf16 [B*L, H*64], lse2 fp32 [B,H,L])."""
     _req(qkv, torch.bfloat16, "qkv")
@@ -65,8 +69,27 @@ def attn_fwd(qkv, B, L, H, scale=None, o=None, lse2=None):
     if o is None:
         o = torch.empty((B * L, D), device=qkv.device, dtype=torch.bfloat16)
     if lse2 is None:
-        lse2 = torch.empty((B, H, L), device=qkv.device, dtype=torch.float32)
+        lse2 = torch.empty((B, H, lpad(L)), device=qkv.device, dtype=torch.float32)
     scale = 64 ** -0.5 if scale is None else scale
     check(_lib.lib().dcv_attn_fwd(ptr(qkv), ptr(o), ptr(lse2), B, L, H, ctypes.c_float(scale), stream_ptr()),
           "dcv_attn_fwd")
     return o, lse2
+
+
+def attn_bwd(qkv, o, do, lse2, B, L, H, scale=None, dqkv=None, delta=None, dq_acc=None):
+    """-> dqkv bf16 [B*L, 3*H*64]."""
+    for t, n in ((qkv, "qkv"), (o, "o"), (do, "do")):
+        _req(t, torch.bfloat16, n)
+        assert t.is_contiguous()
+    D = H * 64
+    dev = qkv.device
+    if dqkv is None:
+        dqkv = torch.empty((B * L, 3 * D), device=dev, dtype=torch.bfloat16)
+    if delta is None:
+        delta = torch.empty((B, H, lpad(L)), device=dev, dtype=torch.float32)
+    if dq_acc is None:
+        dq_acc = torch.empty((B, H, L, 64), device=dev, dtype=torch.float32)
+    scale = 64 ** -0.5 if scale is None else scale
+    check(_lib.lib().dcv_attn_bwd(ptr(qkv), ptr(o), ptr(do), ptr(lse2), ptr(delta), ptr(dq_acc), ptr(dqkv), B, L, H,
+                                  ctypes.c_float(scale), stream_ptr()), "dcv_attn_bwd")
+    return dqkv

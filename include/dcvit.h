@@ -57,9 +57,15 @@ int dcv_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout,
 
 /* Multi-head self-attention forward, head_dim 64: o = softmax(q k^T * scale) v.
  * qkv bf16 [B, L, 3*H*64] (columns q|k|v, head h at h*64), o bf16 [B, L, H*64],
- * lse2 fp32 [B, H, L] = log2-domain log-sum-exp of the scaled scores (saved for backward).
+ * lse2 fp32 [B, H, Lp] (Lp = L rounded up to 128) = log2-domain log-sum-exp of the scaled scores (saved for backward).
  * Replaces models/vit.py:123-141 (q @ k^T * scale, softmax, attn @ v, transpose/reshape). */
 int dcv_attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, void* stream);
+
+/* Attention backward: dqkv bf16 [B, L, 3*H*64] from (qkv, o, dO, lse2).
+ * Workspaces (caller-owned): delta fp32 [B, H, Lp]; dq_acc fp32 [B, H, L, 64] (zeroed inside).
+ * Replaces the autograd backward of models/vit.py:126-141. */
+int dcv_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
+                 void* dqkv, int B, int L, int H, float scale, void* stream);
 
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);

@@ -30,7 +30,7 @@ def fwd_case(B, L, H, mag=1.0):
     torch.cuda.synchronize()
     ro, rl = ref_attn(qkv, B, L, H)
     a = stats(f"fwd o   B{B} L{L} H{H}", o, ro)
-    b = stats(f"fwd lse B{B} L{L} H{H}", lse, rl, 1e-3)
+    b = stats(f"fwd lse B{B} L{L} H{H}", lse[:, :, :L], rl, 1e-3)
     return a < 2e-2 and b < 1e-3
 
 ok = True
@@ -58,3 +58,39 @@ if ok:
         q, k, v = qkv.reshape(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
         ms_t = bench(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
         print(f"attn fwd B{B} L{L}: {ms*1e3:.1f} us = {fl/ms/1e9:.1f} TFLOP/s (torch sdpa {ms_t*1e3:.1f} us = {fl/ms_t/1e9:.1f})", flush=True)
+
+# ---------------- backward ----------------
+def bwd_case(B, L, H, mag=1.0):
+    D = H * 64
+    qkv = (torch.randn(B * L, 3 * D, device=dev) * mag).bfloat16()
+    do = (torch.randn(B * L, D, device=dev)).bfloat16()
+    o, lse = K.attn_fwd(qkv, B, L, H)
+    dqkv = K.attn_bwd(qkv, o, do, lse, B, L, H)
+    torch.cuda.synchronize()
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.reshape(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    ro = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * L, D)
+    ro.backward(do.float())
+    g = x.grad
+    ok = True
+    for nm, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        ok &= stats(f"bwd {nm} B{B} L{L} H{H}", dqkv[:, sl], g[:, sl], 3e-2) < 3e-2
+    return ok
+
+okb = True
+for (B, L, H, mag) in [(1, 128, 1, 1.0), (2, 197, 3, 1.0), (2, 589, 6, 2.0), (1, 1569, 6, 1.0), (3, 81, 3, 2.0), (2, 17, 3, 1.0)]:
+    try:
+        okb &= bwd_case(B, L, H, mag)
+    except Exception as ex:
+        print("BWD FAILED", (B, L, H), repr(ex)); okb = False; break
+print("ATTN BWD ok" if okb else "ATTN BWD BAD", flush=True)
+if okb:
+    for (B, L, H) in [(32, 1569, 6), (32, 785, 6), (128, 289, 6)]:
+        D = H * 64
+        qkv = torch.randn(B * L, 3 * D, device=dev).bfloat16(); do = torch.randn(B * L, D, device=dev).bfloat16()
+        o, lse = K.attn_fwd(qkv, B, L, H)
+        dqkv = torch.empty_like(qkv); delta = torch.empty(B, H, K.lpad(L), device=dev); acc = torch.empty(B, H, L, 64, device=dev)
+        ms = bench(lambda: K.attn_bwd(qkv, o, do, lse, B, L, H, dqkv=dqkv, delta=delta, dq_acc=acc))
+        fl = 8.0 * B * H * L * L * 64
+        print(f"attn bwd B{B} L{L}: {ms*1e3:.1f} us = {fl/ms/1e9:.1f} TFLOP/s (algorithmic 8*L^2*D)", flush=True)
