@@ -100,7 +100,13 @@ int dcv_gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, in
                 const float* bias, void* out, void* out2, const float* resid, const void* aux, int ldo,
                 void* stream) {
   if (!A || !B) return set_error(DCV_ERR_INVALID, "dcv_gemm_nt: null operand");
-  return gemm_nt(A, lda, B, ldb, M, N, K, epilogue, bias, out, out2, resid, aux, ldo, ST(stream));
+  return gemm_nt(A, lda, B, ldb, M, N, K, epilogue, bias, out, out2, resid, aux, ldo, false, ST(stream));
+}
+
+int dcv_gemm_nn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, void* out,
+                const void* aux, int ldo, void* stream) {
+  if (!A || !B) return set_error(DCV_ERR_INVALID, "dcv_gemm_nn: null operand");
+  return gemm_nt(A, lda, B, ldb, M, N, K, epilogue, nullptr, out, nullptr, nullptr, aux, ldo, true, ST(stream));
 }
 
 int dcv_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,

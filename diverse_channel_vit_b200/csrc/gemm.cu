@@ -48,7 +48,7 @@ struct NtCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool kBMn>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const GemmNtParams p) {
@@ -106,7 +106,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(smem_a + stage * (kBM * kBK * 2), &map_a, &full_bar[stage], kb * kBK, m0);
-          tma_load_2d(smem_b + stage * (BN * kBK * 2), &map_b, &full_bar[stage], kb * kBK, n0);
+          if (kBMn) {
+            // B stored [K rows][N cols] (e.g. a weight W[out,in] used as dY*W): MN-major boxes of
+            // [64 reduction rows][64 output columns]
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(smem_b + stage * (BN * kBK * 2) + c * (64 * 128), &map_b, &full_bar[stage], n0 + c * 64,
+                          kb * kBK);
+          } else {
+            tma_load_2d(smem_b + stage * (BN * kBK * 2), &map_b, &full_bar[stage], kb * kBK, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -114,7 +123,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, kBMn ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -127,11 +136,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = make_desc_kmajor(smem_u32(smem_a + stage * (kBM * kBK * 2)));
-          const uint64_t db = make_desc_kmajor(smem_u32(smem_b + stage * (BN * kBK * 2)));
+          const uint32_t sb_addr = smem_u32(smem_b + stage * (BN * kBK * 2));
+          const uint64_t db = kBMn ? make_desc_mnmajor(sb_addr, 64 * 128) : make_desc_kmajor(sb_addr);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes per 16-element K step inside the swizzle atom (encoded >> 4)
-            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            // K-major: +32 bytes per 16-element K step inside the swizzle atom (encoded >> 4);
+            // MN-major: 16 reduction rows = 2048 bytes
+            umma_ss(d_tmem, da + 2 * k, db + (kBMn ? 128 : 2) * k, idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -390,10 +401,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ---------------------------------------------------------------------------
 static int g_tn_lbo = 0, g_tn_sbo = 0;  // debug overrides (0 = default)
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool kBMn>
 static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p, cudaStream_t st) {
   using Cfg = NtCfg<BN>;
-  auto kern = gemm_nt_kernel<BN, EPI>;
+  auto kern = gemm_nt_kernel<BN, EPI, kBMn>;
   static bool attr_done = false;
   if (!attr_done) {
     DCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -408,20 +419,29 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
 }
 
 template <int BN>
-static int dispatch_nt_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p,
+static int dispatch_nt_epi(int epi, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p,
                            cudaStream_t st) {
+  if (b_mn) {  // dgrad flavours only
+    switch (epi) {
+      case EPI_BIAS: return launch_nt<BN, EPI_BIAS, true>(ma, mb, p, st);
+      case EPI_DGELU: return launch_nt<BN, EPI_DGELU, true>(ma, mb, p, st);
+      case EPI_F32: return launch_nt<BN, EPI_F32, true>(ma, mb, p, st);
+    }
+    return set_error(DCV_ERR_UNSUPPORTED, "gemm_nn: epilogue %d not instantiated", epi);
+  }
   switch (epi) {
-    case EPI_BIAS: return launch_nt<BN, EPI_BIAS>(ma, mb, p, st);
-    case EPI_BIAS_GELU: return launch_nt<BN, EPI_BIAS_GELU>(ma, mb, p, st);
-    case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID>(ma, mb, p, st);
-    case EPI_DGELU: return launch_nt<BN, EPI_DGELU>(ma, mb, p, st);
-    case EPI_F32: return launch_nt<BN, EPI_F32>(ma, mb, p, st);
+    case EPI_BIAS: return launch_nt<BN, EPI_BIAS, false>(ma, mb, p, st);
+    case EPI_BIAS_GELU: return launch_nt<BN, EPI_BIAS_GELU, false>(ma, mb, p, st);
+    case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID, false>(ma, mb, p, st);
+    case EPI_DGELU: return launch_nt<BN, EPI_DGELU, false>(ma, mb, p, st);
+    case EPI_F32: return launch_nt<BN, EPI_F32, false>(ma, mb, p, st);
   }
   return set_error(DCV_ERR_INVALID, "gemm_nt: unknown epilogue %d", epi);
 }
 
+// b_mn = false: B is [N][K] (K contiguous);  b_mn = true: B is [K][N] (N contiguous)
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
-            void* out, void* out2, const float* resid, const void* aux, int ldo, cudaStream_t st) {
+            void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(DCV_ERR_INVALID, "gemm_nt: empty problem %dx%dx%d", M, N, K);
   if (K % 8 || lda % 8 || ldb % 8 || ldo % 8)
     return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: K/lda/ldb/ldo must be multiples of 8 (16-byte rows)");
@@ -432,7 +452,11 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   else return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: N=%d must be a multiple of 64", N);
   CUtensorMap ma, mb;
   if (int e = make_tmap_bf16_2d(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM)) return e;
-  if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, bn)) return e;
+  if (b_mn) {
+    if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, kBK)) return e;
+  } else {
+    if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, bn)) return e;
+  }
   GemmNtParams p;
   p.M = M; p.N = N; p.K = K; p.ldo = ldo; p.bias = bias;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out);
@@ -443,9 +467,9 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   if ((epi == EPI_BIAS_GELU && !out2) || (epi == EPI_BIAS_RESID && !resid) || (epi == EPI_DGELU && !aux) || !out)
     return set_error(DCV_ERR_INVALID, "gemm_nt: missing buffer for epilogue %d", epi);
   switch (bn) {
-    case 192: return dispatch_nt_epi<192>(epi, ma, mb, p, st);
-    case 128: return dispatch_nt_epi<128>(epi, ma, mb, p, st);
-    default: return dispatch_nt_epi<64>(epi, ma, mb, p, st);
+    case 192: return dispatch_nt_epi<192>(epi, b_mn, ma, mb, p, st);
+    case 128: return dispatch_nt_epi<128>(epi, b_mn, ma, mb, p, st);
+    default: return dispatch_nt_epi<64>(epi, b_mn, ma, mb, p, st);
   }
 }
 

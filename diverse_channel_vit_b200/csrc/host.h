@@ -30,7 +30,7 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1,
 
 // ---- gemm.cu ----
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
-            void* out, void* out2, const float* resid, const void* aux, int ldo, cudaStream_t st);
+            void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st);
 int gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
             int accumulate, int splits, cudaStream_t st);
 void debug_set_tn_desc(int lbo, int sbo);

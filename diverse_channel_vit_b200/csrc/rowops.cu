@@ -1,0 +1,293 @@
+// HBM-bound row kernels of the transformer blocks: LayerNorm forward/backward
+// (reference models/vit.py:384,398 norm1/norm2 and models/dichavit.py:651 norm;
+// nn.LayerNorm, eps 1e-6, biased variance), bias-gradient column sums, and the
+// fp32 -> bf16 parameter cast.  One warp owns one row; all loads/stores are 8- or
+// 16-byte vectors, coalesced across the warp.
+#include "common.cuh"
+#include "host.h"
+
+namespace dcv {
+
+constexpr int kRowWarps = 8;  // warps per CTA
+
+// ---------------------------------------------------------------------------------
+// LayerNorm forward: x fp32 [M,D] -> y bf16 [M,D], mean/rstd fp32 [M]
+// ---------------------------------------------------------------------------------
+template <int NV>  // float4 per lane, NV = ceil(D / 128)
+__global__ void __launch_bounds__(kRowWarps * 32)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int M, int D,
+              float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D >> 2;
+  float4 g[NV], bt[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int idx = lane + 32 * k;
+    if (idx < nvec) {
+      g[k] = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+      bt[k] = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+    } else {
+      g[k] = make_float4(0, 0, 0, 0);
+      bt[k] = make_float4(0, 0, 0, 0);
+    }
+  }
+  const float inv_d = 1.0f / static_cast<float>(D);
+  for (int row = blockIdx.x * kRowWarps + warp; row < M; row += gridDim.x * kRowWarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = lane + 32 * k;
+      v[k] = idx < nvec ? xr[idx] : make_float4(0, 0, 0, 0);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mu = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < nvec) {
+        const float a = v[k].x - mu, b = v[k].y - mu, c = v[k].z - mu, d = v[k].w - mu;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv_d + eps);
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < nvec) {
+        uint2 o;
+        o.x = pack_bf16((v[k].x - mu) * rs * g[k].x + bt[k].x, (v[k].y - mu) * rs * g[k].y + bt[k].y);
+        o.y = pack_bf16((v[k].z - mu) * rs * g[k].z + bt[k].z, (v[k].w - mu) * rs * g[k].w + bt[k].w);
+        yr[idx] = o;
+      }
+    }
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// LayerNorm backward, fused with the residual-stream gradient add:
+//   dx_out = dres + LN'(dy)       (fp32, in place on dres) and a bf16 copy for the next GEMMs
+//   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dxsum += sum_rows dx_out (bias grad of the
+//   Linear whose output fed this residual add)
+// Persistent grid; per-lane column accumulators, one smem reduction + D atomics per CTA.
+// ---------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dres,
+              __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dxsum, int M, int D) {
+  extern __shared__ float red[];  // [kRowWarps][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D >> 2;
+  float4 g[NV], acc_g[NV], acc_b[NV], acc_s[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int idx = lane + 32 * k;
+    g[k] = idx < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + idx) : make_float4(0, 0, 0, 0);
+    acc_g[k] = acc_b[k] = acc_s[k] = make_float4(0, 0, 0, 0);
+  }
+  const float inv_d = 1.0f / static_cast<float>(D);
+  for (int row = blockIdx.x * kRowWarps + warp; row < M; row += gridDim.x * kRowWarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
+    float4* dr = reinterpret_cast<float4*>(dres + static_cast<size_t>(row) * D);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], gy[NV], dyv[NV];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < nvec) {
+        const float4 xv = xr[idx];
+        const uint2 d2 = dyr[idx];
+        const float2 d01 = unpack_bf16(d2.x), d23 = unpack_bf16(d2.y);
+        dyv[k] = make_float4(d01.x, d01.y, d23.x, d23.y);
+        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        gy[k] = make_float4(dyv[k].x * g[k].x, dyv[k].y * g[k].y, dyv[k].z * g[k].z, dyv[k].w * g[k].w);
+        c1 += (gy[k].x + gy[k].y) + (gy[k].z + gy[k].w);
+        c2 += (gy[k].x * xh[k].x + gy[k].y * xh[k].y) + (gy[k].z * xh[k].z + gy[k].w * xh[k].w);
+      } else {
+        xh[k] = gy[k] = dyv[k] = make_float4(0, 0, 0, 0);
+      }
+    }
+    c1 = warp_sum(c1) * inv_d;
+    c2 = warp_sum(c2) * inv_d;
+    uint2* dxb = reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < nvec) {
+        float4 o = dr[idx];
+        o.x += rs * (gy[k].x - c1 - xh[k].x * c2);
+        o.y += rs * (gy[k].y - c1 - xh[k].y * c2);
+        o.z += rs * (gy[k].z - c1 - xh[k].z * c2);
+        o.w += rs * (gy[k].w - c1 - xh[k].w * c2);
+        dr[idx] = o;
+        uint2 ob;
+        ob.x = pack_bf16(o.x, o.y);
+        ob.y = pack_bf16(o.z, o.w);
+        dxb[idx] = ob;
+        acc_g[k].x += dyv[k].x * xh[k].x; acc_g[k].y += dyv[k].y * xh[k].y;
+        acc_g[k].z += dyv[k].z * xh[k].z; acc_g[k].w += dyv[k].w * xh[k].w;
+        acc_b[k].x += dyv[k].x; acc_b[k].y += dyv[k].y; acc_b[k].z += dyv[k].z; acc_b[k].w += dyv[k].w;
+        acc_s[k].x += o.x; acc_s[k].y += o.y; acc_s[k].z += o.z; acc_s[k].w += o.w;
+      }
+    }
+  }
+  // CTA reduction of the three column accumulators, one after the other through `red`
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    float* target = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+    if (target == nullptr) continue;  // uniform across the CTA
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < nvec) {
+        const float4 a = which == 0 ? acc_g[k] : (which == 1 ? acc_b[k] : acc_s[k]);
+        reinterpret_cast<float4*>(red + warp * D)[idx] = a;
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) t += red[w * D + c];
+      atomicAdd(target + c, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// column sums of a bf16 matrix: out[n] += sum_m a[m,n]   (bias gradients of qkv / fc1)
+// grid (ceil(N/256), row_splits); each warp reads 512 contiguous bytes of a row
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowWarps * 32)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ out, int M, int N, int lda) {
+  __shared__ float red[kRowWarps][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const bool col_ok = col < N;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per;
+  const int r1 = min(M, r0 + rows_per);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col_ok) {
+    for (int r = r0 + warp; r < r1; r += kRowWarps) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + static_cast<size_t>(r) * lda + col));
+      const float2 a0 = unpack_bf16(v.x), a1 = unpack_bf16(v.y), a2 = unpack_bf16(v.z), a3 = unpack_bf16(v.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;  // 256 threads == 256 columns
+  if (blockIdx.x * 256 + c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowWarps; ++w) t += red[w][c];
+    atomicAdd(out + blockIdx.x * 256 + c, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// fp32 -> bf16 cast of the flat parameter buffer (once per optimiser step)
+// ---------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+static int nv_for(int D) { return (D + 127) / 128; }
+
+int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D,
+           float eps, cudaStream_t st) {
+  if (M <= 0 || D <= 0) return set_error(DCV_ERR_INVALID, "ln_fwd: empty problem");
+  if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "ln_fwd: D=%d must be a multiple of 4", D);
+  const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 8);
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (nv_for(D)) {
+    case 1: ln_fwd_kernel<1><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
+    case 2: ln_fwd_kernel<2><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
+    case 3: ln_fwd_kernel<3><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
+    case 6: ln_fwd_kernel<6><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
+    default: return set_error(DCV_ERR_UNSUPPORTED, "ln_fwd: D=%d not instantiated (128/256/384/768 classes)", D);
+  }
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dres,
+           void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int M, int D, cudaStream_t st) {
+  if (M <= 0 || D <= 0) return set_error(DCV_ERR_INVALID, "ln_bwd: empty problem");
+  if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "ln_bwd: D=%d must be a multiple of 4", D);
+  const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 2);
+  const size_t smem = static_cast<size_t>(kRowWarps) * D * sizeof(float);
+  const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define LNB(NV)                                                                                                  \
+  ln_bwd_kernel<NV><<<blocks, kRowWarps * 32, smem, st>>>(dyb, x, mean, rstd, gamma, dres, dxb, dgamma, dbeta, \
+                                                           dxsum, M, D)
+  switch (nv_for(D)) {
+    case 1: LNB(1); break;
+    case 2: LNB(2); break;
+    case 3: LNB(3); break;
+    case 6: LNB(6); break;
+    default: return set_error(DCV_ERR_UNSUPPORTED, "ln_bwd: D=%d not instantiated", D);
+  }
+#undef LNB
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int colsum_bf16(const void* a, float* out, int M, int N, int lda, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return set_error(DCV_ERR_INVALID, "colsum: empty problem");
+  if (N % 8 || lda % 8) return set_error(DCV_ERR_UNSUPPORTED, "colsum: N and lda must be multiples of 8");
+  const int cb = (N + 255) / 256;
+  int splits = (num_sms() * 4 + cb - 1) / cb;
+  if (splits > (M + 31) / 32) splits = (M + 31) / 32;
+  if (splits < 1) splits = 1;
+  colsum_bf16_kernel<<<dim3(cb, splits), kRowWarps * 32, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a), out, M,
+                                                                  N, lda);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return set_error(DCV_ERR_INVALID, "cast: empty");
+  const long long threads = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace dcv

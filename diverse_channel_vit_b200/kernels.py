@@ -44,6 +44,21 @@ def gemm_nt(a, b, epilogue=EPI_BIAS, bias=None, out=None, out2=None, resid=None,
     return (out, out2) if epilogue == EPI_BIAS_GELU else out
 
 
+def gemm_nn(a, b, epilogue=EPI_BIAS, out=None, aux=None):
+    """out = a[M,K] @ b[K,N] (b row-major, no transpose copy); epilogue BIAS(plain)/DGELU/F32."""
+    _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16)
+    if aux is not None:
+        assert aux.stride(0) == out.stride(0)
+    check(_lib.lib().dcv_gemm_nn(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, epilogue, ptr(out), ptr(aux),
+                                 out.stride(0), stream_ptr()), "dcv_gemm_nn")
+    return out
+
+
 def gemm_tn(a, b, out=None, accumulate=True, splits=0):
     """out[Nout,Kout] (+)= a[M,Nout]^T @ b[M,Kout]; fp32 output."""
     _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")

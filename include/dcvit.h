@@ -48,6 +48,13 @@ int dcv_gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, in
                 const float* bias, void* out, void* out2, const float* resid, const void* aux, int ldo,
                 void* stream);
 
+/* C[M,N] = A[M,K] * B[K,N]; A bf16 [M,K], B bf16 [K,N] row-major (consumed MN-major, no transposed
+ * copy).  epilogue in {DCV_EPI_BIAS (no bias: plain bf16 store), DCV_EPI_DGELU, DCV_EPI_F32}.
+ * Replaces the autograd input gradient of nn.Linear (dX = dY W) and, with DCV_EPI_DGELU, the
+ * GELU backward of models/vit.py:77-78. */
+int dcv_gemm_nn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, void* out,
+                const void* aux, int ldo, void* stream);
+
 /* C[Nout,Kout] (+)= A[M,Nout]^T * B[M,Kout]; A, B bf16 row-major, C fp32.
  * accumulate=1: split-K atomic accumulation into C (caller zero-fills or holds a
  * running gradient); accumulate=0: plain store, single split.  splits<=0: auto.
