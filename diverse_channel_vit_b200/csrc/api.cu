@@ -127,6 +127,75 @@ int dcv_attn_bwd(const void* qkv, const void* o, const void* dO, const float* ls
   return attn_bwd(qkv, o, dO, lse2, delta, dq_acc, dqkv, B, L, H, scale, ST(stream));
 }
 
+int dcv_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
+               int D, float eps, void* stream) {
+  if (!x || !gamma || !beta || !y || !mean || !rstd) return set_error(DCV_ERR_INVALID, "dcv_ln_fwd: null pointer");
+  return ln_fwd(x, gamma, beta, y, mean, rstd, M, D, eps, ST(stream));
+}
+
+int dcv_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+               float* dres, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int M, int D, void* stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !dres || !dx_bf16 || !dgamma || !dbeta)
+    return set_error(DCV_ERR_INVALID, "dcv_ln_bwd: null pointer");
+  return ln_bwd(dy, x, mean, rstd, gamma, dres, dx_bf16, dgamma, dbeta, dxsum, M, D, ST(stream));
+}
+
+int dcv_colsum_bf16(const void* a, float* out, int M, int N, int lda, void* stream) {
+  if (!a || !out) return set_error(DCV_ERR_INVALID, "dcv_colsum_bf16: null pointer");
+  return colsum_bf16(a, out, M, N, lda, ST(stream));
+}
+
+int dcv_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (!src || !dst) return set_error(DCV_ERR_INVALID, "dcv_cast_f32_bf16: null pointer");
+  return cast_f32_bf16(src, dst, n, ST(stream));
+}
+
+int dcv_sgemm_small(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
+                    const float* bias, int accumulate, int M, int N, int K, void* stream) {
+  if (!A || !B || !C) return set_error(DCV_ERR_INVALID, "dcv_sgemm_small: null pointer");
+  return sgemm_small(A, lda, transA, B, ldb, transB, C, ldc, bias, accumulate, M, N, K, ST(stream));
+}
+
+int dcv_block_fwd(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a, void* stream) {
+  if (!dims || !p || !a) return set_error(DCV_ERR_INVALID, "dcv_block_fwd: null struct");
+  return block_fwd(*dims, *p, *a, ST(stream));
+}
+
+int dcv_block_bwd(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a,
+                  const dcv_block_grads* g, const dcv_block_ws* ws, float* dres, void* dres_bf16,
+                  float* dbias_prev, void* stream) {
+  if (!dims || !p || !a || !g || !ws || !dres || !dres_bf16)
+    return set_error(DCV_ERR_INVALID, "dcv_block_bwd: null struct / pointer");
+  return block_bwd(*dims, *p, *a, *g, *ws, dres, dres_bf16, dbias_prev, ST(stream));
+}
+
+int dcv_embed_fwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const float* x,
+                  const int* idx, const int* gid, const dcv_embed_acts* a, void* stream) {
+  if (!dims || !cfg || !p || !a) return set_error(DCV_ERR_INVALID, "dcv_embed_fwd: null struct");
+  return embed_fwd(*dims, *cfg, *p, x, idx, gid, *a, ST(stream));
+}
+
+int dcv_embed_bwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const int* gid,
+                  const dcv_embed_acts* a, const dcv_embed_grads* g, const dcv_embed_ws* ws, const float* G,
+                  const float* d_extra, void* stream) {
+  if (!dims || !cfg || !p || !a || !g || !ws) return set_error(DCV_ERR_INVALID, "dcv_embed_bwd: null struct");
+  return embed_bwd(*dims, *cfg, *p, gid, *a, *g, *ws, G, d_extra, ST(stream));
+}
+
+int dcv_head_fwd(const float* x_last, int B, int L, int D, const float* norm_w, const float* norm_b, float* feat,
+                 float* mean, float* rstd, const float* head_w, const float* head_b, float* logits, int num_classes,
+                 void* stream) {
+  return head_fwd(x_last, B, L, D, norm_w, norm_b, feat, mean, rstd, head_w, head_b, logits, num_classes, ST(stream));
+}
+
+int dcv_head_bwd(const float* d_out, const float* x_last, int B, int L, int D, const float* norm_w,
+                 const float* feat, const float* mean, const float* rstd, const float* head_w, int num_classes,
+                 float* dfeat_ws, float* dres, void* dres_bf16, float* g_norm_w, float* g_norm_b, float* g_head_w,
+                 float* g_head_b, float* dbias_last, void* stream) {
+  return head_bwd(d_out, x_last, B, L, D, norm_w, feat, mean, rstd, head_w, num_classes, dfeat_ws, dres, dres_bf16,
+                  g_norm_w, g_norm_b, g_head_w, g_head_b, dbias_last, ST(stream));
+}
+
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo_bytes, sbo_bytes); }
 
 }  // extern "C"

@@ -27,6 +27,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_RESID = 2,  // out_f32 = resid + acc + bias   (resid may alias out_f32)
   EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux)
   EPI_F32 = 4,         // out_f32 = acc (+ bias)
+  EPI_EMBED = 5,       // out_f32[(m / T) * L + 1 + m % T][:] = acc + addend[m % T][:]   (patch embedding)
 };
 
 struct GemmNtParams {
@@ -38,6 +39,10 @@ struct GemmNtParams {
   float* out_f32;
   const float* resid;
   const __nv_bfloat16* aux;
+  // EPI_EMBED: rows m = (image b, token t) with t in [0,T); the output is the [B, L=T+1, D] token
+  // tensor (row 0 of every image is the CLS token, written elsewhere); addend fp32 [T, ldo]
+  int map_T, map_L;
+  const float* addend;
 };
 
 template <int BN>
@@ -163,7 +168,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const size_t row_off = static_cast<size_t>(row) * p.ldo;
+      size_t row_off = static_cast<size_t>(row) * p.ldo;
+      size_t add_off = 0;
+      if (EPI == EPI_EMBED) {
+        const int bi = row / p.map_T, t = row - bi * p.map_T;
+        row_off = (static_cast<size_t>(bi) * p.map_L + 1 + t) * p.ldo;
+        add_off = static_cast<size_t>(t) * p.ldo;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -173,7 +184,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (EPI != EPI_DGELU && p.bias != nullptr) {
+        if (EPI != EPI_DGELU && EPI != EPI_EMBED && p.bias != nullptr) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
@@ -219,10 +230,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               o.w = pack_bf16(v[8 * i + 6] * gelu_exact_grad(h3.x), v[8 * i + 7] * gelu_exact_grad(h3.y));
               dst[i] = o;
             }
-          } else {  // EPI_BIAS_RESID / EPI_F32
+          } else {  // EPI_BIAS_RESID / EPI_F32 / EPI_EMBED
             float4* dst = reinterpret_cast<float4*>(p.out_f32 + row_off + col0);
-            if (EPI == EPI_BIAS_RESID) {
-              const float4* rs = reinterpret_cast<const float4*>(p.resid + row_off + col0);
+            if (EPI == EPI_BIAS_RESID || EPI == EPI_EMBED) {
+              const float4* rs = EPI == EPI_EMBED ? reinterpret_cast<const float4*>(p.addend + add_off + col0)
+                                                  : reinterpret_cast<const float4*>(p.resid + row_off + col0);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 r4 = rs[i];
@@ -435,13 +447,15 @@ static int dispatch_nt_epi(int epi, bool b_mn, const CUtensorMap& ma, const CUte
     case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID, false>(ma, mb, p, st);
     case EPI_DGELU: return launch_nt<BN, EPI_DGELU, false>(ma, mb, p, st);
     case EPI_F32: return launch_nt<BN, EPI_F32, false>(ma, mb, p, st);
+    case EPI_EMBED: return launch_nt<BN, EPI_EMBED, false>(ma, mb, p, st);
   }
   return set_error(DCV_ERR_INVALID, "gemm_nt: unknown epilogue %d", epi);
 }
 
 // b_mn = false: B is [N][K] (K contiguous);  b_mn = true: B is [K][N] (N contiguous)
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
-            void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st) {
+            void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st,
+            int map_T, int map_L, const float* addend) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(DCV_ERR_INVALID, "gemm_nt: empty problem %dx%dx%d", M, N, K);
   if (K % 8 || lda % 8 || ldb % 8 || ldo % 8)
     return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: K/lda/ldb/ldo must be multiples of 8 (16-byte rows)");
@@ -464,6 +478,9 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   p.out_f32 = reinterpret_cast<float*>(out);
   p.resid = resid;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
+  p.map_T = map_T; p.map_L = map_L; p.addend = addend;
+  if (epi == EPI_EMBED && (!addend || map_T <= 0 || map_L <= map_T || M % map_T))
+    return set_error(DCV_ERR_INVALID, "gemm_nt: EPI_EMBED needs addend, T>0, L>T, M %% T == 0");
   if ((epi == EPI_BIAS_GELU && !out2) || (epi == EPI_BIAS_RESID && !resid) || (epi == EPI_DGELU && !aux) || !out)
     return set_error(DCV_ERR_INVALID, "gemm_nt: missing buffer for epilogue %d", epi);
   switch (bn) {

@@ -30,7 +30,8 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1,
 
 // ---- gemm.cu ----
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
-            void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st);
+            void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st,
+            int map_T = 0, int map_L = 0, const float* addend = nullptr);
 int gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
             int accumulate, int splits, cudaStream_t st);
 void debug_set_tn_desc(int lbo, int sbo);
@@ -39,5 +40,57 @@ void debug_set_tn_desc(int lbo, int sbo);
 int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st);
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
              void* dqkv, int B, int L, int H, float scale, cudaStream_t st);
+
+// ---- rowops.cu ----
+int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D,
+           float eps, cudaStream_t st);
+int ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dres,
+           void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int M, int D, cudaStream_t st);
+int colsum_bf16(const void* a, float* out, int M, int N, int lda, cudaStream_t st);
+int colsum_f32(const float* a, float* out, int M, int N, int lda, cudaStream_t st);
+int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st);
+
+// ---- embed.cu ----
+int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, int Cs, int H, int W, int P,
+                  cudaStream_t st);
+int embed_addend(const float* bias, const float* chan_embed, const int* gid, const float* pos_patch, const float* cls,
+                 const float* pos0, float* addend, float* tokens, int B, int Cs, int N, int D, cudaStream_t st);
+int tdl_fwd(const float* tokens, const float* addend, const float* bias, float* S, float* Q, float* rnorm,
+            float* S_all, float* loss_b, float* coef_pos, float* coef_neg, float* tdl_out, int B, int Cs, int N, int D,
+            float gamma_s, float gamma_d, int reverse_pos_pairs, int use_square, cudaStream_t st);
+int embed_bwd_dy(const float* G, const float* tokens, const float* addend, const float* bias, const float* rnorm,
+                 const float* S, const float* S_all, const float* coef_pos, const float* coef_neg,
+                 const float* d_extra, float lambda_tdl, void* dY, int B, int Cs, int N, int D, cudaStream_t st);
+int embed_param_grads(const float* G, float* R, const int* gid, float* d_cls, float* d_pos0, float* d_chan_embed,
+                      float* dpos_patch, int accumulate_pos, int B, int Cs, int N, int D, cudaStream_t st);
+int cdl_fwd(const float* chan_embed, const float* proxies, const int* gid, float scale, float* loss, float* dE,
+            float* dP, int Cs, int D, cudaStream_t st);
+int cdl_bwd(const float* dE, const float* dP, const int* gid, const float* d_extra, float lambda_cdl,
+            float* g_chan_embed, float* g_proxies, int Cs, int D, cudaStream_t st);
+int extra_loss(const float* tdl, const float* cdl, float lt, float lc, float* extra, cudaStream_t st);
+int sgemm_small(const float* A, int lda, int transA, const float* Bm, int ldb, int transB, float* C, int ldc,
+                const float* bias, int accumulate, int M, int N, int K, cudaStream_t st);
+int cls_ln_fwd(const float* x, long long row_stride, const float* gamma, const float* beta, float* feat, float* mean,
+               float* rstd, int B, int D, float eps, cudaStream_t st);
+int cls_ln_bwd(const float* dfeat, const float* x, long long row_stride, const float* mean, const float* rstd,
+               const float* gamma, float* dres, void* dres_bf16, float* dgamma, float* dbeta, float* dxsum, int B,
+               int D, cudaStream_t st);
+
+// ---- model.cu (stage orchestration behind dcv_block_* / dcv_embed_* / dcv_head_*) ----
+int block_fwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, cudaStream_t st);
+int block_bwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, const dcv_block_grads& g,
+              const dcv_block_ws& ws, float* dres, void* dres_bf16, float* dbias_prev, cudaStream_t st);
+int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const float* x,
+              const int* idx, const int* gid, const dcv_embed_acts& a, cudaStream_t st);
+int embed_bwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const int* gid,
+              const dcv_embed_acts& a, const dcv_embed_grads& g, const dcv_embed_ws& ws, const float* G,
+              const float* d_extra, cudaStream_t st);
+int head_fwd(const float* x_last, int B, int L, int D, const float* norm_w, const float* norm_b, float* feat,
+             float* mean, float* rstd, const float* head_w, const float* head_b, float* logits, int num_classes,
+             cudaStream_t st);
+int head_bwd(const float* d_out, const float* x_last, int B, int L, int D, const float* norm_w, const float* feat,
+             const float* mean, const float* rstd, const float* head_w, int num_classes, float* dfeat_ws, float* dres,
+             void* dres_bf16, float* g_norm_w, float* g_norm_b, float* g_head_w, float* g_head_b, float* dbias_last,
+             cudaStream_t st);
 
 }  // namespace dcv

@@ -203,6 +203,15 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ out,
   }
 }
 
+// out[n] += sum_m a[m,n], a fp32 [M,N] with a handful of rows (classifier-head bias gradient)
+__global__ void colsum_f32_kernel(const float* __restrict__ a, float* __restrict__ out, int M, int N, int lda) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int m = 0; m < M; ++m) t += a[static_cast<size_t>(m) * lda + n];
+  out[n] += t;
+}
+
 // ---------------------------------------------------------------------------------
 // fp32 -> bf16 cast of the flat parameter buffer (once per optimiser step)
 // ---------------------------------------------------------------------------------
@@ -275,6 +284,14 @@ int colsum_bf16(const void* a, float* out, int M, int N, int lda, cudaStream_t s
   if (splits < 1) splits = 1;
   colsum_bf16_kernel<<<dim3(cb, splits), kRowWarps * 32, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a), out, M,
                                                                   N, lda);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int colsum_f32(const float* a, float* out, int M, int N, int lda, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return set_error(DCV_ERR_INVALID, "colsum_f32: empty problem");
+  colsum_f32_kernel<<<(N + 127) / 128, 128, 0, st>>>(a, out, M, N, lda);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

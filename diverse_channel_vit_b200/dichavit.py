@@ -1,0 +1,778 @@
+"""Drop-in `DiChaViT` module (reference models/dichavit.py:748-865) whose forward and backward run
+entirely in the hand-written sm_100a kernels of libdcvit.so (C ABI: include/dcvit.h).
+
+Same constructor (`DiChaViT(config, mapper=...)`, factory `dichavit(cfg, **kw)`), same parameter
+names / shapes / state_dict keys (154 for ViT-S), same forward signature and return convention
+(train: `(out, extra_loss)`, eval: `out`), same host-visible attributes (`proxies`, `scale`,
+`feature_extractor.patch_embed.counter`, `.mapper`).  There is no CPU / PyTorch fallback: calling
+the module with a non-CUDA tensor or without the built library raises.
+
+PyTorch is used for: parameter storage (one flat fp32 buffer, nn.Parameters are views into it),
+the caching allocator (activation arena), streams, the DCS probability / `torch.multinomial` draw
+(kept as the reference's own ATen ops so the sampled indices are bit-identical for a given RNG
+state) and `torch.distributed` for the data-parallel gradient all-reduce.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import random
+from collections import Counter
+from ctypes import POINTER, Structure, byref, c_float, c_int, c_longlong, c_void_p
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import DcvError, check
+
+_SIZES = {  # reference models/dichavit.py:676-745
+    "tiny": (192, 3),
+    "small": (384, 6),
+    "distill": (384, 6),
+    "base": (768, 12),
+}
+_DEPTH = 12
+_MLP_RATIO = 4
+
+
+# ---------------------------------------------------------------------------------------------
+# ctypes mirrors of the structs in include/dcvit.h
+# ---------------------------------------------------------------------------------------------
+class _Dims(Structure):
+    _fields_ = [(n, c_int) for n in ("B", "L", "D", "H", "F")]
+
+
+class _BlockParams(Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_b", "proj_b", "ln2_w", "ln2_b", "fc1_b", "fc2_b",
+                                        "qkv_w", "proj_w", "fc1_w", "fc2_w")]
+
+
+class _BlockGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b",
+                                        "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class _BlockActs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("x_in", "u", "mean1", "rstd1", "qkv", "o", "lse2", "x_mid", "v", "mean2",
+                                        "rstd2", "h", "g", "x_out")]
+
+
+class _BlockWs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("dh", "dv", "d_o", "dqkv", "delta", "dq_acc")]
+
+
+class _EmbedDims(Structure):
+    _fields_ = [(n, c_int) for n in ("B", "C", "Cs", "H", "W", "P", "D")]
+
+
+class _EmbedCfg(Structure):
+    _fields_ = [("lambda_tdl", c_float), ("lambda_cdl", c_float), ("gamma_s", c_float), ("gamma_d", c_float),
+                ("cdl_scale", c_float), ("reverse_pos_pairs", c_int), ("use_square", c_int)]
+
+
+class _EmbedParams(Structure):
+    _fields_ = [(n, c_void_p) for n in ("proj_w", "proj_b", "chan_embed", "proxies", "cls", "pos", "pos_map")]
+
+
+class _EmbedGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in ("proj_w", "proj_b", "chan_embed", "proxies", "cls", "pos")]
+
+
+class _EmbedActs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("patches", "pos_patch", "addend", "tokens", "S", "Q", "rnorm", "S_all",
+                                        "loss_b", "coef_pos", "coef_neg", "cdl_dE", "cdl_dP", "tdl", "cdl", "extra")]
+
+
+class _EmbedWs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("dY", "R", "dpos_patch")]
+
+
+def _trunc_normal_(t: torch.Tensor, std: float = 0.02, a: float = -2.0, b: float = 2.0) -> torch.Tensor:
+    """Truncated normal init, same RNG consumption as reference utils.py:477-517 (uniform -> erfinv)."""
+    def cdf(v):
+        return (1.0 + math.erf(v / math.sqrt(2.0))) / 2.0
+
+    with torch.no_grad():
+        lo, hi = cdf(a / std), cdf(b / std)
+        t.uniform_(2 * lo - 1, 2 * hi - 1)
+        t.erfinv_()
+        t.mul_(std * math.sqrt(2.0))
+        t.clamp_(min=a, max=b)
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers (never executed; they only own parameters under the reference's names)
+# ---------------------------------------------------------------------------------------------
+class _Attention(nn.Module):  # reference models/vit.py:101-119
+    def __init__(self, dim: int):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):  # reference models/vit.py:59-74
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):  # reference models/vit.py:346-381
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _Attention(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim, hidden)
+
+
+class _LazyCounter:
+    """`patch_embed.counter` (reference dichavit.py:66-67,214-216; read by trainer.py:796-804): how often
+    each global channel id was sampled.  Counts accumulate on the device; they are copied to the host only
+    when somebody reads them, so the training step has no device->host sync."""
+
+    def __init__(self, n_channels: int):
+        self.n = n_channels
+        self._dev: Optional[torch.Tensor] = None
+        self._host = np.zeros(n_channels, dtype=np.int64)
+
+    def add(self, gid: torch.Tensor) -> None:
+        if self._dev is None or self._dev.device != gid.device:
+            self._flush()
+            self._dev = torch.zeros(self.n, dtype=torch.int64, device=gid.device)
+        self._dev.index_add_(0, gid.long(), torch.ones_like(gid, dtype=torch.int64))
+
+    def add_host(self, ids: Sequence[int]) -> None:
+        for k, v in Counter(ids).items():
+            self._host[k] += v
+
+    def _flush(self) -> None:
+        if self._dev is not None:
+            self._host += self._dev.cpu().numpy()
+            self._dev.zero_()
+
+    def as_dict(self) -> Dict[int, int]:
+        self._flush()
+        return {int(i): int(v) for i, v in enumerate(self._host) if v > 0}
+
+    def items(self):
+        return self.as_dict().items()
+
+    def keys(self):
+        return self.as_dict().keys()
+
+    def values(self):
+        return self.as_dict().values()
+
+    def __getitem__(self, k):
+        return self.as_dict().get(k, 0)
+
+    def __iter__(self):
+        return iter(self.as_dict())
+
+    def __len__(self):
+        return len(self.as_dict())
+
+
+class PatchEmbedPerChannel(nn.Module):
+    """Parameters + DCS index selection of reference models/dichavit.py:39-216."""
+
+    def __init__(self, config, img_size: int, patch_size: int, in_chans: int, mapper, embed_dim: int,
+                 enable_sample: bool, use_channelvit_channels: bool = True):
+        super().__init__()
+        self.cfg = config
+        self.img_size = img_size
+        self.mapper = mapper
+        self.patch_size = patch_size
+        self.num_patches = (img_size // patch_size) * (img_size // patch_size) * in_chans
+        self.channel_scale = np.sqrt(1.0 / config.temperature)
+        if config.proxy_loss_lambda > 0:
+            self.channel_emb_proxies = nn.Parameter(torch.randn(in_chans, embed_dim) / 8)
+            if config.get("proxy_orthogonal_init", False):
+                nn.init.orthogonal_(self.channel_emb_proxies)
+        if config.hcs_sampling != "none" and config.hcs_sampling is not None:
+            self.counter = _LazyCounter(in_chans)
+        if not isinstance(config.hcs_sampling, str) and config.hcs_sampling is not None:
+            raise ValueError("hcs_sampling must be a string")
+        self.proj = nn.Conv3d(1, embed_dim, kernel_size=(1, patch_size, patch_size),
+                              stride=(1, patch_size, patch_size))
+        if not use_channelvit_channels:
+            raise NotImplementedError("use_channelvit_channels=False is outside the DiChaViT hot path")
+        self.channel_embed = nn.Embedding(in_chans, embed_dim)
+        if config.orthogonal_channel_emb_init:
+            nn.init.orthogonal_(self.channel_embed.weight)
+        else:
+            _trunc_normal_(self.channel_embed.weight, std=0.02)
+        if config.freeze_channel_emb:
+            self.channel_embed.weight.requires_grad = False
+        self.use_channelvit_channels = use_channelvit_channels
+        self.enable_sample = enable_sample
+        self._chan_cache: Dict[tuple, torch.Tensor] = {}
+
+    def chunk_channels(self, chunk_name: str, device) -> torch.Tensor:
+        key = (chunk_name, tuple(self.mapper[chunk_name]), str(device))
+        t = self._chan_cache.get(key)
+        if t is None:
+            t = torch.tensor(list(self.mapper[chunk_name]), dtype=torch.int64, device=device)
+            self._chan_cache[key] = t
+        return t
+
+    def select_channels(self, chunk_name: str, n_in: int, device):
+        """DCS (reference dichavit.py:127-216).  Returns (C', idx int32 [C'] or None, gid int32 [C']):
+        positions of the kept channels inside x, and their global channel ids, both on `device`.
+        RNG consumption is the reference's: random.randint(1,C), random.randint(0,C-1), then
+        torch.multinomial on the device generator.  Nothing is copied back to the host."""
+        chan = self.chunk_channels(chunk_name, device)
+        if chan.numel() != n_in:
+            raise ValueError(f"x has {n_in} channels but mapper['{chunk_name}'] lists {chan.numel()}")
+        if not (self.training and self.enable_sample):
+            return n_in, None, chan.to(torch.int32)
+        mode = self.cfg.hcs_sampling
+        c_new = random.randint(1, n_in)
+        if mode == "none" or mode is None:
+            cur = random.sample(list(self.mapper[chunk_name]), k=c_new)
+            pos = [list(self.mapper[chunk_name]).index(c) for c in cur]
+            idx = torch.tensor(pos, dtype=torch.int32, device=device)
+            return c_new, idx, torch.tensor(cur, dtype=torch.int32, device=device)
+        if mode == "hcs_per_sample":
+            raise ValueError("hcs_per_sample not implemented!")  # as the reference, dichavit.py:394-395
+        if mode not in ("lowest_cosine_prob", "lowest_cosine", "highest_cosine"):
+            raise NotImplementedError(f"hcs_sampling='{mode}' is outside the DiChaViT hot path")
+        with torch.no_grad():
+            anchor = random.randint(0, n_in - 1)
+            emb = self.channel_embed.weight[chan]
+            emb_n = F.normalize(emb, p=2, dim=-1)
+            cosine = torch.einsum("c d, e d -> c e", emb_n, emb_n)[anchor]
+            if mode == "lowest_cosine_prob":
+                prob = F.softmax((1 - cosine) / self.cfg.hcs_sampling_temp, dim=-1)
+                indices = torch.multinomial(prob, c_new, replacement=False)
+            else:
+                indices = torch.topk(cosine, k=c_new, largest=(mode == "highest_cosine"))[1]
+            # `if anchor not in indices: indices[-1] = anchor` (dichavit.py:201-202), on the device
+            anchor_t = torch.full((), anchor, dtype=indices.dtype, device=device)
+            last = torch.where((indices == anchor).any(), indices[-1], anchor_t)
+            indices = torch.cat((indices[:-1], last[None]))
+            gid = chan[indices]
+            self.counter.add(gid)
+        return c_new, indices.to(torch.int32), gid.to(torch.int32)
+
+
+class ChannelVisionTransformer(nn.Module):
+    """Parameter layout of reference models/dichavit.py:420-516."""
+
+    def __init__(self, config, img_size, patch_size: int, in_chans: int, mapper, embed_dim: int, depth: int,
+                 num_heads: int, mlp_ratio: int, enable_sample: bool, use_channelvit_channels: bool = True):
+        super().__init__()
+        self.cfg = config
+        if config.drop_path_rate != 0:
+            raise NotImplementedError("drop_path_rate != 0 is outside the DiChaViT hot path (reference default 0.0)")
+        if config.block_type != "block":
+            if config.block_type == "block_v2":
+                raise NotImplementedError("block_type=block_v2 (token pruning) is outside the DiChaViT hot path")
+            raise ValueError(f"Unknown block type: {config.block_type}")
+        if config.dropout_tokens_hcs not in ("none", None):
+            raise NotImplementedError("dropout_tokens_hcs != none is outside the DiChaViT hot path")
+        self.num_features = self.embed_dim = self.out_dim = embed_dim
+        self.in_chans = in_chans
+        self.num_heads = num_heads
+        img = img_size[0] if isinstance(img_size, (list, tuple)) or hasattr(img_size, "__getitem__") else img_size
+        self.patch_embed = PatchEmbedPerChannel(config, img, patch_size, in_chans, mapper, embed_dim, enable_sample,
+                                                use_channelvit_channels)
+        num_patches = self.patch_embed.num_patches
+        self.patch_size = patch_size
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.num_extra_tokens = 1
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches // in_chans + 1, embed_dim))
+        self.blocks = nn.ModuleList([_Block(embed_dim, int(embed_dim * mlp_ratio)) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.head = nn.Identity()
+        _trunc_normal_(self.pos_embed, std=0.02)
+        _trunc_normal_(self.cls_token, std=0.02)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):  # reference dichavit.py:509-516
+        if isinstance(m, nn.Linear):
+            _trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+
+def bicubic_pos_matrix(grid: int, w: int, h: int, patch: int) -> torch.Tensor:
+    """The fixed linear map of reference dichavit.py:531-549: F.interpolate(mode="bicubic") of the
+    [grid, grid] positional grid with scale ((w//P + 0.1)/grid, (h//P + 0.1)/grid), as an explicit
+    [N_out, N_in] fp32 matrix (identity pushed through the same ATen call, once, on the host)."""
+    n_in = grid * grid
+    w0, h0 = w // patch + 0.1, h // patch + 0.1
+    eye = torch.eye(n_in, dtype=torch.float32).reshape(1, grid, grid, n_in).permute(0, 3, 1, 2)
+    out = F.interpolate(eye, scale_factor=(w0 / grid, h0 / grid), mode="bicubic")
+    if int(w0) != out.shape[-2] or int(h0) != out.shape[-1]:
+        raise ValueError("bicubic positional resample produced an unexpected grid")
+    return out.permute(0, 2, 3, 1).reshape(-1, n_in).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# flat parameter store
+# ---------------------------------------------------------------------------------------------
+_ALIGN = 64  # elements: 256 B in fp32, 128 B in bf16 (TMA needs 16 B)
+
+
+def _round_up(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
+class _Arena:
+    """Carves one uint8 torch allocation into 256-byte aligned raw pointers."""
+
+    def __init__(self):
+        self.off = 0
+        self.slots: Dict[str, int] = {}
+
+    def add(self, name: str, nbytes: int) -> None:
+        self.slots[name] = self.off
+        self.off += _round_up(max(int(nbytes), 4), 256)
+
+    def alloc(self, device) -> torch.Tensor:
+        return torch.empty(max(self.off, 256), dtype=torch.uint8, device=device)
+
+
+class DiChaViT(nn.Module):
+    def __init__(self, config, **kwargs):
+        super().__init__()
+        self.cfg = config
+        mapper = kwargs["mapper"]
+        name = config.pretrained_model_name
+        if name not in _SIZES:
+            raise ValueError("Unknown model name")
+        dim, heads = _SIZES[name]
+        total_in_channels = len(config.in_channel_names)
+        self.feature_extractor = ChannelVisionTransformer(
+            config, img_size=config.img_size, patch_size=config.patch_size, in_chans=total_in_channels, mapper=mapper,
+            embed_dim=dim, depth=_DEPTH, num_heads=heads, mlp_ratio=_MLP_RATIO, enable_sample=config.enable_sample,
+            use_channelvit_channels=config.use_channelvit_channels)
+        self.classifer_head = nn.Identity()
+        if "Allen" not in mapper:
+            self.classifer_head = nn.Linear(dim, config.num_classes)
+        self.dim = dim
+        self.proxies = nn.Parameter(torch.randn(config.num_classes, dim) / 8)
+        if config.learnable_temp:
+            self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / config.temperature))
+        else:
+            self.scale = np.sqrt(1.0 / config.temperature)
+        self.adaptive_interface = nn.ParameterList([self.proxies])
+
+        # engine state
+        self._flat: Optional[torch.Tensor] = None      # fp32 master parameters
+        self._bflat: Optional[torch.Tensor] = None     # bf16 copy, refreshed every forward
+        self._layout: List[tuple] = []                 # (param, offset, numel)
+        self._groups: List[tuple] = []                 # (name, start, end) gradient buckets in backward order
+        self._pos_maps: Dict[tuple, torch.Tensor] = {}
+        self.grad_allreduce = False                    # set by enable_data_parallel()
+        self._pg = None
+        self._comm_stream = None
+        self.last_losses: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ parameters
+    def _ordered_params(self):
+        fe = self.feature_extractor
+        pe = fe.patch_embed
+        embed = [fe.cls_token, fe.pos_embed]
+        if hasattr(pe, "channel_emb_proxies"):
+            embed.append(pe.channel_emb_proxies)
+        embed += [pe.proj.weight, pe.proj.bias, pe.channel_embed.weight]
+        groups = [("embed", embed)]
+        for i, b in enumerate(fe.blocks):
+            groups.append((f"block{i}", [b.norm1.weight, b.norm1.bias, b.attn.qkv.weight, b.attn.qkv.bias,
+                                         b.attn.proj.weight, b.attn.proj.bias, b.norm2.weight, b.norm2.bias,
+                                         b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias]))
+        tail = [fe.norm.weight, fe.norm.bias]
+        if isinstance(self.classifer_head, nn.Linear):
+            tail += [self.classifer_head.weight, self.classifer_head.bias]
+        tail.append(self.proxies)
+        if hasattr(self, "logit_scale"):
+            tail.append(self.logit_scale)
+        groups.append(("tail", tail))
+        return groups
+
+    def _ensure_flat(self, device) -> None:
+        ok = self._flat is not None and self._flat.device == device
+        if ok:
+            base = self._flat.data_ptr()
+            for p, off, n in self._layout:
+                if p.data_ptr() != base + 4 * off or p.dtype != torch.float32:
+                    ok = False
+                    break
+        if ok:
+            return
+        groups = self._ordered_params()
+        layout, bounds, off = [], [], 0
+        for gname, plist in groups:
+            start = off
+            for p in plist:
+                layout.append((p, off, p.numel()))
+                off += _round_up(p.numel(), _ALIGN)
+            bounds.append((gname, start, off))
+        flat = torch.zeros(off, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, o, n in layout:
+                if p.device != device:
+                    raise DcvError(f"parameter on {p.device}, input on {device}: move the module with .to(device)")
+                flat[o:o + n].copy_(p.detach().reshape(-1).float())
+                p.data = flat[o:o + n].view(p.shape)
+        self._flat, self._layout, self._groups = flat, layout, bounds
+        self._bflat = torch.empty(off, dtype=torch.bfloat16, device=device)
+        self._off = {id(p): o for p, o, _ in layout}
+
+    def _fptr(self, p) -> int:
+        return self._flat.data_ptr() + 4 * self._off[id(p)]
+
+    def _bptr(self, p) -> int:
+        return self._bflat.data_ptr() + 2 * self._off[id(p)]
+
+    def _pos_map(self, w: int, h: int, device) -> torch.Tensor:
+        fe = self.feature_extractor
+        n = fe.pos_embed.shape[1] - 1
+        key = (w, h, str(device))
+        m = self._pos_maps.get(key)
+        if m is None:
+            m = bicubic_pos_matrix(int(math.sqrt(n)), w, h, fe.patch_size).to(device)
+            self._pos_maps[key] = m
+        return m
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, process_group=None, overlap: bool = True) -> "DiChaViT":
+        """Batch-sharded data parallelism (replaces DDP at reference trainer.py:1185): gradient buckets
+        are all-reduced (average) with NCCL on a side stream as soon as the backward of the layers they
+        cover has been enqueued, overlapping the remaining backward."""
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise DcvError("torch.distributed is not initialised")
+        self.grad_allreduce = True
+        self._pg = process_group
+        self._overlap = overlap
+        return self
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, chunk_name: str, training_chunks: Optional[str] = None, init_first_layer=None,
+                new_channel_init=None, **kwargs):
+        if not x.is_cuda:
+            raise DcvError("DiChaViT (B200-native) needs a CUDA tensor: there is no CPU fallback")
+        if x.dim() != 4:
+            raise ValueError("x must be [B, C, H, W]")
+        if training_chunks is not None and new_channel_init is not None:
+            self._check_leave_one_out(chunk_name, training_chunks)
+        x = x.contiguous().float()
+        self._ensure_flat(x.device)
+        pe = self.feature_extractor.patch_embed
+        cs, idx, gid = pe.select_channels(chunk_name, x.shape[1], x.device)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p, _, _ in self._layout)
+        params = [p for p, _, _ in self._layout]
+        out, extra = _DiChaViTFn.apply(self, x, cs, idx, gid, need_grad, *params)
+        if self.training:
+            return out, extra
+        return out
+
+    def _check_leave_one_out(self, chunk_name, training_chunks):
+        """reference dichavit.py:219-374: channel-token synthesis for channels unseen in training.  For every
+        published config the test channels are a subset of the training channels, where that branch reduces to
+        the plain lookup done here; anything else is rejected instead of silently diverging."""
+        pe = self.feature_extractor.patch_embed
+        train_ch = set()
+        for c in str(training_chunks).split("_"):
+            if c in pe.mapper:
+                train_ch.update(pe.mapper[c])
+        if train_ch and not set(pe.mapper[chunk_name]).issubset(train_ch):
+            raise NotImplementedError("leave-one-out channel synthesis (new_channel_inits) is not implemented yet")
+
+    # ------------------------------------------------------------------ engine
+    def _plan(self, B: int, cs: int, H: int, W: int, keep: bool):
+        fe = self.feature_extractor
+        P, D, heads = fe.patch_size, self.dim, fe.num_heads
+        N = (H // P) * (W // P)
+        T = cs * N
+        L = T + 1
+        M = B * L
+        Fh = D * _MLP_RATIO
+        Lp = _round_up(L, 128)
+        depth = len(fe.blocks)
+        ar = _Arena()
+        ar.add("patches", B * T * P * P * 2)
+        ar.add("pos_patch", N * D * 4)
+        ar.add("addend", T * D * 4)
+        for nm, sz in (("S", B * cs * D), ("Q", B * cs), ("rnorm", B * T), ("S_all", B * D), ("loss_b", B),
+                       ("coef_pos", B), ("coef_neg", B), ("cdl_dE", cs * D), ("cdl_dP", cs * D)):
+            ar.add(nm, sz * 4)
+        ar.add("head_mean", B * 4)
+        ar.add("head_rstd", B * 4)
+        nsets = depth if keep else 1
+        nx = depth + 1 if keep else 2
+        for i in range(nx):
+            ar.add(f"x{i}", M * D * 4)
+        for i in range(nsets):
+            ar.add(f"u{i}", M * D * 2)
+            ar.add(f"mean1_{i}", M * 4)
+            ar.add(f"rstd1_{i}", M * 4)
+            ar.add(f"qkv{i}", M * 3 * D * 2)
+            ar.add(f"o{i}", M * D * 2)
+            ar.add(f"lse{i}", B * heads * Lp * 4)
+            ar.add(f"xmid{i}", M * D * 4)
+            ar.add(f"v{i}", M * D * 2)
+            ar.add(f"mean2_{i}", M * 4)
+            ar.add(f"rstd2_{i}", M * 4)
+            ar.add(f"h{i}", M * Fh * 2)
+            ar.add(f"g{i}", M * Fh * 2)
+        return dict(B=B, cs=cs, H=H, W=W, P=P, D=D, heads=heads, N=N, T=T, L=L, M=M, F=Fh, Lp=Lp, depth=depth,
+                    arena=ar, keep=keep)
+
+    def _embed_structs(self, pl, base: int, scal: torch.Tensor, C_in: int, use_map: bool, device):
+        fe = self.feature_extractor
+        pe = fe.patch_embed
+        cfg = self.cfg
+        s = pl["arena"].slots
+        dims = _EmbedDims(pl["B"], C_in, pl["cs"], pl["H"], pl["W"], pl["P"], pl["D"])
+        ecfg = _EmbedCfg(float(cfg.ortho_loss_v1_lambda), float(cfg.proxy_loss_lambda), float(cfg.gamma_s),
+                         float(cfg.gamma_d), float(pe.channel_scale), int(bool(cfg.reverse_pos_pairs)),
+                         int(bool(cfg.use_square)))
+        has_prox = hasattr(pe, "channel_emb_proxies")
+        pos_map = self._pos_map(pl["W"], pl["H"], device) if use_map else None
+        ep = _EmbedParams(self._bptr(pe.proj.weight), self._fptr(pe.proj.bias), self._fptr(pe.channel_embed.weight),
+                          self._fptr(pe.channel_emb_proxies) if has_prox else None, self._fptr(fe.cls_token),
+                          self._fptr(fe.pos_embed), pos_map.data_ptr() if pos_map is not None else None)
+        sp = scal.data_ptr()
+        acts = _EmbedActs(base + s["patches"], base + s["pos_patch"], base + s["addend"], base + s["x0"],
+                          base + s["S"], base + s["Q"], base + s["rnorm"], base + s["S_all"], base + s["loss_b"],
+                          base + s["coef_pos"], base + s["coef_neg"], base + s["cdl_dE"], base + s["cdl_dP"],
+                          sp, sp + 4, sp + 8)
+        return dims, ecfg, ep, acts, pos_map
+
+    def _block_structs(self, pl, base: int, i: int):
+        s = pl["arena"].slots
+        keep = pl["keep"]
+        k = i if keep else 0
+        xin = f"x{i}" if keep else f"x{i % 2}"
+        xout = f"x{i + 1}" if keep else f"x{(i + 1) % 2}"
+        b = self.feature_extractor.blocks[i]
+        bp = _BlockParams(self._fptr(b.norm1.weight), self._fptr(b.norm1.bias), self._fptr(b.attn.qkv.bias),
+                          self._fptr(b.attn.proj.bias), self._fptr(b.norm2.weight), self._fptr(b.norm2.bias),
+                          self._fptr(b.mlp.fc1.bias), self._fptr(b.mlp.fc2.bias), self._bptr(b.attn.qkv.weight),
+                          self._bptr(b.attn.proj.weight), self._bptr(b.mlp.fc1.weight), self._bptr(b.mlp.fc2.weight))
+        ba = _BlockActs(base + s[xin], base + s[f"u{k}"], base + s[f"mean1_{k}"], base + s[f"rstd1_{k}"],
+                        base + s[f"qkv{k}"], base + s[f"o{k}"], base + s[f"lse{k}"], base + s[f"xmid{k}"],
+                        base + s[f"v{k}"], base + s[f"mean2_{k}"], base + s[f"rstd2_{k}"], base + s[f"h{k}"],
+                        base + s[f"g{k}"], base + s[xout])
+        return bp, ba, xout
+
+    def _run_forward(self, x: torch.Tensor, cs: int, idx, gid, keep: bool):
+        lib = _lib.lib()
+        st = _lib.stream_ptr()
+        dev = x.device
+        B, C_in, H, W = x.shape
+        fe = self.feature_extractor
+        n_pos = fe.pos_embed.shape[1] - 1
+        P = fe.patch_size
+        if (H // P) * (W // P) != n_pos:
+            raise ValueError(f"input {H}x{W} does not match the {n_pos}-patch positional grid")
+        pl = self._plan(B, cs, H, W, keep)
+        # fp32 master -> bf16 operand copy of every parameter (one launch)
+        check(lib.dcv_cast_f32_bf16(c_void_p(self._flat.data_ptr()), c_void_p(self._bflat.data_ptr()),
+                                    c_longlong(self._flat.numel()), st), "dcv_cast_f32_bf16")
+        arena = pl["arena"].alloc(dev)
+        base = arena.data_ptr()
+        scal = torch.zeros(4, dtype=torch.float32, device=dev)  # tdl, cdl, extra
+        # reference dichavit.py:529-530: raw pos_embed iff the token count equals the grid and w == h
+        use_map = not (cs * pl["N"] == n_pos and W == H)
+        dims, ecfg, ep, eacts, pos_map = self._embed_structs(pl, base, scal, C_in, use_map, dev)
+        check(lib.dcv_embed_fwd(byref(dims), byref(ecfg), byref(ep), c_void_p(x.data_ptr()),
+                                c_void_p(idx.data_ptr()) if idx is not None else None, c_void_p(gid.data_ptr()),
+                                byref(eacts), st), "dcv_embed_fwd")
+        bd = _Dims(B, pl["L"], pl["D"], pl["heads"], pl["F"])
+        last = "x0"
+        for i in range(pl["depth"]):
+            bp, ba, last = self._block_structs(pl, base, i)
+            check(lib.dcv_block_fwd(byref(bd), byref(bp), byref(ba), st), "dcv_block_fwd")
+        D = pl["D"]
+        s = pl["arena"].slots
+        feat = torch.empty((B, D), dtype=torch.float32, device=dev)
+        head = self.classifer_head if isinstance(self.classifer_head, nn.Linear) else None
+        ncls = head.out_features if head is not None else 0
+        logits = torch.empty((B, ncls), dtype=torch.float32, device=dev) if head is not None else None
+        check(lib.dcv_head_fwd(c_void_p(base + s[last]), B, pl["L"], D, c_void_p(self._fptr(fe.norm.weight)),
+                               c_void_p(self._fptr(fe.norm.bias)), c_void_p(feat.data_ptr()),
+                               c_void_p(base + s["head_mean"]), c_void_p(base + s["head_rstd"]),
+                               c_void_p(self._fptr(head.weight)) if head is not None else None,
+                               c_void_p(self._fptr(head.bias)) if head is not None else None,
+                               c_void_p(logits.data_ptr()) if logits is not None else None, ncls, st), "dcv_head_fwd")
+        self.last_losses = {"tdl": scal[0], "cdl": scal[1], "extra": scal[2]}
+        state = dict(pl=pl, arena=arena, scal=scal, x=x, idx=idx, gid=gid, feat=feat, last=last, C_in=C_in,
+                     use_map=use_map, pos_map=pos_map) if keep else None
+        out = logits if head is not None else feat
+        return out, scal[2], state
+
+    def _run_backward(self, state, d_out: Optional[torch.Tensor], d_extra: Optional[torch.Tensor]):
+        lib = _lib.lib()
+        st = _lib.stream_ptr()
+        pl = state["pl"]
+        dev = state["x"].device
+        B, D, L, M, Fh, heads, Lp, T = pl["B"], pl["D"], pl["L"], pl["M"], pl["F"], pl["heads"], pl["Lp"], pl["T"]
+        fe = self.feature_extractor
+        pe = fe.patch_embed
+        base = state["arena"].data_ptr()
+        s = pl["arena"].slots
+        gflat = torch.zeros_like(self._flat)
+        gb = gflat.data_ptr()
+
+        def gp(p):
+            return gb + 4 * self._off[id(p)]
+
+        ws = _Arena()
+        ws.add("dres", M * D * 4)
+        ws.add("dres_b", M * D * 2)
+        ws.add("dh", max(M * Fh * 2, B * T * D * 2))
+        ws.add("dv", M * D * 2)
+        ws.add("d_o", M * D * 2)
+        ws.add("dqkv", M * 3 * D * 2)
+        ws.add("delta", B * heads * Lp * 4)
+        ws.add("dq_acc", B * heads * L * 64 * 4)
+        ws.add("R", L * D * 4)
+        ws.add("dpos_patch", pl["N"] * D * 4)
+        ws.add("dfeat", B * D * 4)
+        wbuf = ws.alloc(dev)
+        wb = wbuf.data_ptr()
+        w = ws.slots
+        head = self.classifer_head if isinstance(self.classifer_head, nn.Linear) else None
+        ncls = head.out_features if head is not None else 0
+        if d_out is None:
+            d_out = torch.zeros((B, ncls if head is not None else D), dtype=torch.float32, device=dev)
+        d_out = d_out.contiguous().float()
+        last_blk = fe.blocks[-1]
+        check(lib.dcv_head_bwd(c_void_p(d_out.data_ptr()), c_void_p(base + s[state["last"]]), B, L, D,
+                               c_void_p(self._fptr(fe.norm.weight)), c_void_p(state["feat"].data_ptr()),
+                               c_void_p(base + s["head_mean"]), c_void_p(base + s["head_rstd"]),
+                               c_void_p(self._fptr(head.weight)) if head is not None else None, ncls,
+                               c_void_p(wb + w["dfeat"]), c_void_p(wb + w["dres"]), c_void_p(wb + w["dres_b"]),
+                               c_void_p(gp(fe.norm.weight)), c_void_p(gp(fe.norm.bias)),
+                               c_void_p(gp(head.weight)) if head is not None else None,
+                               c_void_p(gp(head.bias)) if head is not None else None,
+                               c_void_p(gp(last_blk.mlp.fc2.bias)), st), "dcv_head_bwd")
+        reducer = _GradReducer(self, gflat) if self.grad_allreduce else None
+        if reducer:
+            reducer.ready("tail", flush=True)
+        bd = _Dims(B, L, D, heads, Fh)
+        bws = _BlockWs(wb + w["dh"], wb + w["dv"], wb + w["d_o"], wb + w["dqkv"], wb + w["delta"], wb + w["dq_acc"])
+        for i in reversed(range(pl["depth"])):
+            bp, ba, _ = self._block_structs(pl, base, i)
+            b = fe.blocks[i]
+            bg = _BlockGrads(gp(b.norm1.weight), gp(b.norm1.bias), gp(b.attn.qkv.weight), gp(b.attn.qkv.bias),
+                             gp(b.attn.proj.weight), gp(b.attn.proj.bias), gp(b.norm2.weight), gp(b.norm2.bias),
+                             gp(b.mlp.fc1.weight), gp(b.mlp.fc1.bias), gp(b.mlp.fc2.weight), gp(b.mlp.fc2.bias))
+            prev_bias = gp(fe.blocks[i - 1].mlp.fc2.bias) if i > 0 else None
+            check(lib.dcv_block_bwd(byref(bd), byref(bp), byref(ba), byref(bg), byref(bws), c_void_p(wb + w["dres"]),
+                                    c_void_p(wb + w["dres_b"]), c_void_p(prev_bias) if prev_bias else None, st),
+                  "dcv_block_bwd")
+            if reducer:
+                reducer.ready(f"block{i}")
+        dims, ecfg, ep, eacts, _ = self._embed_structs(pl, base, state["scal"], state["C_in"], state["use_map"], dev)
+        has_prox = hasattr(pe, "channel_emb_proxies")
+        eg = _EmbedGrads(gp(pe.proj.weight), gp(pe.proj.bias), gp(pe.channel_embed.weight),
+                         gp(pe.channel_emb_proxies) if has_prox else None, gp(fe.cls_token), gp(fe.pos_embed))
+        ews = _EmbedWs(wb + w["dh"], wb + w["R"], wb + w["dpos_patch"])
+        if d_extra is not None:
+            d_extra = d_extra.contiguous().float()
+        check(lib.dcv_embed_bwd(byref(dims), byref(ecfg), byref(ep), c_void_p(state["gid"].data_ptr()), byref(eacts),
+                                byref(eg), byref(ews), c_void_p(wb + w["dres"]),
+                                c_void_p(d_extra.data_ptr()) if d_extra is not None else None, st), "dcv_embed_bwd")
+        if reducer:
+            reducer.ready("embed", flush=True)
+            reducer.finish()
+        grads = []
+        for p, off, n in self._layout:
+            grads.append(gflat[off:off + n].view(p.shape) if p.requires_grad else None)
+        return grads
+
+
+class _GradReducer:
+    """Bucketed NCCL all-reduce(avg) of the flat gradient buffer on a side stream, overlapped with the rest
+    of backward.  The flat buffer is laid out embed | block0 .. block11 | tail and backward completes it from
+    the top down, so the finished-but-unreduced region is always one contiguous range."""
+
+    BUCKET_BLOCKS = 3
+
+    def __init__(self, module: "DiChaViT", gflat: torch.Tensor):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.m = module
+        self.g = gflat
+        self.bounds = {n: (a, b) for n, a, b in module._groups}
+        self.overlap = bool(getattr(module, "_overlap", True))
+        if module._comm_stream is None:
+            module._comm_stream = torch.cuda.Stream(device=gflat.device)
+        self.stream = module._comm_stream
+        self.works = []
+        self.lo: Optional[int] = None
+        self.hi: Optional[int] = None
+        self.n = 0
+
+    def _launch(self, lo: int, hi: int) -> None:
+        if hi <= lo:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            self.works.append(self.dist.all_reduce(self.g[lo:hi], op=self.dist.ReduceOp.AVG, group=self.m._pg,
+                                                   async_op=True))
+
+    def ready(self, name: str, flush: bool = False) -> None:
+        """The gradients of parameter group `name` are complete on the current stream."""
+        if not self.overlap:
+            return
+        a, b = self.bounds[name]
+        self.lo = a if self.lo is None else min(self.lo, a)
+        self.hi = b if self.hi is None else max(self.hi, b)
+        self.n += 1
+        if flush or self.n >= self.BUCKET_BLOCKS:
+            self._launch(self.lo, self.hi)
+            self.lo = self.hi = None
+            self.n = 0
+
+    def finish(self) -> None:
+        if not self.overlap:
+            self._launch(0, self.g.numel())
+        elif self.lo is not None:
+            self._launch(self.lo, self.hi)
+        for wk in self.works:
+            wk.wait()
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class _DiChaViTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module: DiChaViT, x, cs, idx, gid, need_grad, *params):
+        out, extra, state = module._run_forward(x, cs, idx, gid, keep=need_grad)
+        ctx.module = module
+        ctx.state = state
+        ctx.set_materialize_grads(False)
+        return out, extra
+
+    @staticmethod
+    def backward(ctx, d_out, d_extra):
+        if ctx.state is None:
+            raise DcvError("backward called on a forward that ran without gradient tracking")
+        grads = ctx.module._run_backward(ctx.state, d_out, d_extra)
+        ctx.state = None
+        return (None, None, None, None, None, None, *grads)
+
+
+def dichavit(cfg, **kwargs) -> DiChaViT:
+    """Factory registered under the reference's name (models/dichavit.py:864-865, models/__init__.py:9)."""
+    return DiChaViT(config=cfg, **kwargs)

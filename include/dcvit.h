@@ -4,16 +4,19 @@
  * The reference (chaudatascience/diverse_channel_vit) has no FFI: its hot path is
  * the Python nn.Module models/dichavit.py + models/vit.py + models/loss_fn.py that
  * dispatches to ATen.  Every entry point below therefore replaces an ATen call
- * site of that module; the reference file:line each one stands in for is cited.
+ * site (or a group of them) of that module; the reference file:line each one stands
+ * in for is cited.  Paths are relative to the reference repository root.
  *
  * Conventions
- *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the
- *     name ends in _host.  The caller owns every buffer, including workspaces.
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers.  The caller
+ *     owns every buffer, including activations kept for backward and workspaces.
  *   - `stream` is a cudaStream_t passed as void*.  Functions only enqueue work:
  *     no allocation, no synchronisation, no global mutable state.
  *   - return 0 on success, a negative DCV_ERR_* otherwise; dcv_last_error()
  *     returns a thread-local message for the last failure.
- *   - bf16 buffers are `uint16_t`-sized elements (void* here), fp32 are float*.
+ *   - bf16 buffers are void*, fp32 are float*.  "[r, c]" is row-major.
+ *   - token tensors are [B, L, D] with L = 1 + C'*N: row 0 CLS, row 1 + c*N + p =
+ *     patch p of the c-th sampled channel (reference dichavit.py:414-415, :561-562).
  */
 #ifndef DCVIT_H_
 #define DCVIT_H_
@@ -34,6 +37,8 @@ int dcv_version(void);
 /* number of kernels launched by this library since load (bench.py "gpu_launches") */
 long long dcv_launch_count(void);
 
+/* =============================== primitive operators =============================== */
+
 /* ---- epilogues of dcv_gemm_nt ---- */
 #define DCV_EPI_BIAS 0       /* out(bf16) = A*B^T (+ bias)                                  */
 #define DCV_EPI_BIAS_GELU 1  /* out(bf16) = h = A*B^T + bias ; out2(bf16) = gelu_erf(h)      */
@@ -43,7 +48,7 @@ long long dcv_launch_count(void);
 
 /* C[M,N] = A[M,K] * B[N,K]^T with a fused epilogue; A, B bf16 row-major.
  * Replaces nn.Linear forward (models/vit.py:116 qkv, :118 proj, :71 fc1 + :65 GELU,
- * :73 fc2, residual adds :397-398) and the autograd dgrad of the same layers. */
+ * :73 fc2, residual adds :397-398). */
 int dcv_gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue,
                 const float* bias, void* out, void* out2, const float* resid, const void* aux, int ldo,
                 void* stream);
@@ -64,7 +69,8 @@ int dcv_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout,
 
 /* Multi-head self-attention forward, head_dim 64: o = softmax(q k^T * scale) v.
  * qkv bf16 [B, L, 3*H*64] (columns q|k|v, head h at h*64), o bf16 [B, L, H*64],
- * lse2 fp32 [B, H, Lp] (Lp = L rounded up to 128) = log2-domain log-sum-exp of the scaled scores (saved for backward).
+ * lse2 fp32 [B, H, Lp] (Lp = L rounded up to 128) = log2-domain log-sum-exp of the scaled
+ * scores (saved for backward).
  * Replaces models/vit.py:123-141 (q @ k^T * scale, softmax, attn @ v, transpose/reshape). */
 int dcv_attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, void* stream);
 
@@ -73,6 +79,149 @@ int dcv_attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, flo
  * Replaces the autograd backward of models/vit.py:126-141. */
 int dcv_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
                  void* dqkv, int B, int L, int H, float scale, void* stream);
+
+/* LayerNorm forward over rows (nn.LayerNorm, biased variance): x fp32 [M,D] -> y bf16 [M,D],
+ * mean/rstd fp32 [M].  Replaces models/vit.py:384,398 (norm1, norm2; eps 1e-6 dichavit.py:724). */
+int dcv_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
+               int D, float eps, void* stream);
+
+/* LayerNorm backward fused with the residual-stream gradient add:
+ *   dres(fp32, in/out) += LN'(dy);  dx_bf16 = bf16(dres);  dgamma += ..; dbeta += ..;
+ *   dxsum (nullable) += column sums of the updated dres (bias gradient of the Linear that
+ *   produced this residual branch's input).  Replaces autograd of the same lines. */
+int dcv_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+               float* dres, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int M, int D, void* stream);
+
+/* out[n] += sum_m a[m,n], a bf16 [M,N] (bias gradients of qkv / fc1). */
+int dcv_colsum_bf16(const void* a, float* out, int M, int N, int lda, void* stream);
+
+/* dst(bf16)[i] = src(fp32)[i]: the per-step bf16 copy of the flat parameter buffer. */
+int dcv_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+
+/* C[M,N] = (accumulate ? C : 0) + op(A) op(B) (+ bias[N]); tiny fp32 SIMT GEMM used for the
+ * bicubic positional-embedding resample (dichavit.py:518-552, a fixed linear map) and the
+ * classifier head (dichavit.py:801,855).  transA: A stored [K,M]; transB: B stored [N,K]. */
+int dcv_sgemm_small(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
+                    const float* bias, int accumulate, int M, int N, int K, void* stream);
+
+/* =============================== fused stages =============================== */
+
+/* ---- transformer block (models/vit.py:346-399 Block.forward and its autograd) ---- */
+typedef struct dcv_dims {
+  int B, L, D, H, F; /* images, tokens per image, embed dim, heads (D = 64 H), MLP hidden */
+} dcv_dims;
+
+typedef struct dcv_block_params { /* fp32 vectors; bf16 [out, in] weight copies */
+  const float *ln1_w, *ln1_b, *qkv_b, *proj_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;
+  const void *qkv_w, *proj_w, *fc1_w, *fc2_w;
+} dcv_block_params;
+
+typedef struct dcv_block_grads { /* fp32, ACCUMULATED into (caller zero-fills once per step) */
+  float *ln1_w, *ln1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} dcv_block_grads;
+
+typedef struct dcv_block_acts { /* activations written by forward, read by backward; M = B*L rows */
+  const float* x_in; /* fp32 [M, D] block input (owned by the previous stage)       */
+  void* u;           /* bf16 [M, D]  LN1 output                                      */
+  float *mean1, *rstd1;
+  void* qkv;   /* bf16 [M, 3D]                                                        */
+  void* o;     /* bf16 [M, D]  attention output (head-major columns)                  */
+  float* lse2; /* fp32 [B, H, Lp]                                                     */
+  float* x_mid; /* fp32 [M, D]  after the attention residual                          */
+  void* v;      /* bf16 [M, D]  LN2 output                                            */
+  float *mean2, *rstd2;
+  void* h;      /* bf16 [M, F]  fc1 pre-activation                                    */
+  void* g;      /* bf16 [M, F]  gelu(h)                                               */
+  float* x_out; /* fp32 [M, D]  block output                                          */
+} dcv_block_acts;
+
+typedef struct dcv_block_ws { /* backward scratch, reusable across blocks */
+  void* dh;      /* bf16 [M, F]  */
+  void* dv;      /* bf16 [M, D]  (also reused for du) */
+  void* d_o;     /* bf16 [M, D]  */
+  void* dqkv;    /* bf16 [M, 3D] */
+  float* delta;  /* fp32 [B, H, Lp] */
+  float* dq_acc; /* fp32 [B, H, L, 64] */
+} dcv_block_ws;
+
+int dcv_block_fwd(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a, void* stream);
+
+/* dres fp32 [M,D] / dres_bf16 [M,D]: gradient w.r.t. the block output on entry, w.r.t. the block
+ * input on exit.  dbias_prev (nullable): receives += column sums of the exit gradient, i.e. the
+ * bias gradient of the previous block's fc2.  This block's fc2 bias gradient is produced by the
+ * NEXT stage in backward order (the later block's dbias_prev / dcv_head_bwd). */
+int dcv_block_bwd(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a,
+                  const dcv_block_grads* g, const dcv_block_ws* ws, float* dres, void* dres_bf16,
+                  float* dbias_prev, void* stream);
+
+/* ---- channel-adaptive patch embedding + DCS gather + CLS/pos + TDL + CDL ----
+ * models/dichavit.py:110-417 (PatchEmbedPerChannel.forward: x[:, idx] gather :210, Conv3d proj :377,
+ * TDL :378-389, CDL :399-402, extra loss :406-408, + channel_embed :409-411), :554-565 (CLS, pos),
+ * :518-552 (bicubic pos resample), models/loss_fn.py:7-59. */
+typedef struct dcv_embed_dims {
+  int B, C, Cs, H, W, P, D; /* images, channels in x, sampled channels C', image H x W, patch, embed dim */
+} dcv_embed_dims;
+
+typedef struct dcv_embed_cfg {
+  float lambda_tdl, lambda_cdl; /* ortho_loss_v1_lambda, proxy_loss_lambda (0 = loss off) */
+  float gamma_s, gamma_d;
+  float cdl_scale; /* sqrt(1 / temperature), dichavit.py:60 */
+  int reverse_pos_pairs, use_square;
+} dcv_embed_cfg;
+
+typedef struct dcv_embed_params {
+  const void* proj_w;      /* bf16 [D, P*P] (Conv3d weight reshaped)                       */
+  const float* proj_b;     /* [D]                                                          */
+  const float* chan_embed; /* [C_total, D] channel_embed.weight                            */
+  const float* proxies;    /* [C_total, D] channel_emb_proxies (NULL if CDL off)           */
+  const float* cls;        /* [D]                                                          */
+  const float* pos;        /* [1 + N, D] pos_embed                                         */
+  const float* pos_map;    /* [N, N] bicubic resample matrix, NULL = use pos[1:] unchanged */
+} dcv_embed_params;
+
+typedef struct dcv_embed_grads { /* fp32, accumulated */
+  float *proj_w, *proj_b, *chan_embed, *proxies, *cls, *pos;
+} dcv_embed_grads;
+
+typedef struct dcv_embed_acts {
+  void* patches;    /* bf16 [B*C'*N, P*P]  gathered im2col rows (A of the GEMM, B of its wgrad) */
+  float* pos_patch; /* fp32 [N, D]   */
+  float* addend;    /* fp32 [C'*N, D] bias + channel token + positional embedding            */
+  float* tokens;    /* fp32 [B, L, D] output                                                 */
+  float *S, *Q, *rnorm, *S_all, *loss_b, *coef_pos, *coef_neg; /* TDL state: [B,C',D] [B,C'] [B,T] [B,D] [B] [B] [B] */
+  float *cdl_dE, *cdl_dP; /* [C', D] unscaled CDL gradients                                 */
+  float *tdl, *cdl, *extra; /* scalars: TDL, CDL, lambda_tdl*TDL + lambda_cdl*CDL            */
+} dcv_embed_acts;
+
+typedef struct dcv_embed_ws {
+  void* dY;          /* bf16 [B*C'*N, D] */
+  float* R;          /* fp32 [L, D]      */
+  float* dpos_patch; /* fp32 [N, D]      */
+} dcv_embed_ws;
+
+/* x fp32 [B, C, H, W]; idx int32 [C'] positions of the sampled channels inside x (NULL = 0..C'-1);
+ * gid int32 [C'] their global channel ids (rows of chan_embed / proxies). */
+int dcv_embed_fwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const float* x,
+                  const int* idx, const int* gid, const dcv_embed_acts* a, void* stream);
+
+/* G fp32 [B, L, D]: gradient w.r.t. tokens; d_extra: device scalar, gradient w.r.t. the extra loss. */
+int dcv_embed_bwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const int* gid,
+                  const dcv_embed_acts* a, const dcv_embed_grads* g, const dcv_embed_ws* ws, const float* G,
+                  const float* d_extra, void* stream);
+
+/* ---- final norm on the CLS row + classifier head (dichavit.py:651-652, :801, :855) ----
+ * head_w NULL: out = feat (CHAMMI, Identity head); else logits = feat head_w^T + head_b. */
+int dcv_head_fwd(const float* x_last, int B, int L, int D, const float* norm_w, const float* norm_b, float* feat,
+                 float* mean, float* rstd, const float* head_w, const float* head_b, float* logits, int num_classes,
+                 void* stream);
+
+/* d_out fp32 [B, num_classes] (or [B, D] without head).  Zero-fills dres / dres_bf16 [B*L, D] and
+ * writes their CLS rows; accumulates g_norm_w/b, g_head_w/b and (nullable) dbias_last = fc2 bias
+ * gradient of the last block.  dfeat_ws fp32 [B, D] scratch (unused without head). */
+int dcv_head_bwd(const float* d_out, const float* x_last, int B, int L, int D, const float* norm_w,
+                 const float* feat, const float* mean, const float* rstd, const float* head_w, int num_classes,
+                 float* dfeat_ws, float* dres, void* dres_bf16, float* g_norm_w, float* g_norm_b, float* g_head_w,
+                 float* g_head_b, float* dbias_last, void* stream);
 
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);
