@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- DiChaViT training hot path on B200 (metric of BASELINE.json: train images/sec, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload jumpcp|chammi|so2sat|vitb]
+
+Workload at N GPUs (weak scaling, SURVEY.md section 8(d) "C3"): DiChaViT ViT-S/16, JUMP-CP shape (8 channels, 224x224,
+161 classes, 1568 channel-patch tokens at full channels), 32 images per GPU, DCS channel sampling
+(lowest_cosine_prob, temp 1000) + CDL (lambda 0.001) + TDL (lambda 0.001, gamma 1/4), CE loss, seed 2025.
+A step = zero_grad + forward + loss + backward (+ gradient all-reduce for N > 1) + AdamW update, on synthetic
+randn images / randint labels with the module's own random init (datasets and checkpoints are offline).
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: same step driven from pinned HOST
+buffers through the public module API (H2D of the batch and D2H of the loss inside the timed region).
+`roofline`: the dominant kernel class, timed live with CUDA events by the library's built-in profiler in a
+separate pass of the same steps.  `cpu_baseline`: the oracle restatement of the reference (torch fp32, all
+host cores) on a bounded sample.  `--impl reference` prints the reference arm (same CPU path) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "train images/sec (fwd+bwd)"
+UNIT = "images/s"
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+WORKLOADS = {
+    # name: (model size, img, patch, channels, classes, per-GPU batch, hcs temp, lambda_cdl, lambda_tdl, gamma_s, gamma_d, temperature, chammi)
+    "jumpcp": dict(size="small", img=224, patch=16, channels=8, classes=161, batch=32, hcs_temp=1000.0, l_cdl=0.001,
+                   l_tdl=0.001, gs=1.0, gd=4.0, sample=True,
+                   desc="DiChaViT ViT-S/16 JUMP-CP 8ch 224x224 (<=1569 tokens), 32 img/GPU, DCS+CDL+TDL, CE-161"),
+    "so2sat": dict(size="small", img=32, patch=8, channels=18, classes=17, batch=128, hcs_temp=0.01, l_cdl=0.001,
+                   l_tdl=0.1, gs=0.5, gd=4.0, sample=True,
+                   desc="DiChaViT ViT-S/8 So2Sat 18ch 32x32 (<=289 tokens), 128 img/GPU, DCS+CDL+TDL, CE-17"),
+    "vitb": dict(size="base", img=224, patch=16, channels=8, classes=161, batch=16, hcs_temp=0.1, l_cdl=0.0,
+                 l_tdl=0.0, gs=1.0, gd=0.5, sample=False,
+                 desc="DiChaViT ViT-B/16 JUMP-CP 8ch full channels (1569 tokens), 16 img/GPU, CE-161"),
+}
+
+
+def model_cfg(w) -> Cfg:
+    return Cfg(name="dichavit", pretrained=False, pretrained_model_name=w["size"], in_dim=None, num_classes=w["classes"],
+               pooling="avg", temperature=0.11111, learnable_temp=False, unfreeze_last_n_layers=-1,
+               unfreeze_first_layer=True, init_first_layer=None, reset_last_n_unfrozen_layers=False,
+               enable_sample=w["sample"], in_channel_names=[f"c{i}" for i in range(w["channels"])],
+               new_channel_inits=None, use_channelvit_channels=True, patch_size=w["patch"],
+               orthogonal_channel_emb_init=True, dropout_tokens_hcs="none", freeze_channel_emb=False, keep_rate=None,
+               block_type="block", hcs_sampling="lowest_cosine_prob", hcs_sampling_temp=w["hcs_temp"],
+               proxy_loss_lambda=w["l_cdl"], ortho_loss_v1_lambda=w["l_tdl"], drop_path_rate=0.0, gamma_s=w["gs"],
+               gamma_d=w["gd"], reverse_pos_pairs=True, use_square=False, img_size=[w["img"]])
+
+
+def set_seeds(seed: int, cuda: bool):
+    """reference utils.py:394-401"""
+    import numpy as np
+    import torch
+
+    random.seed(seed)
+    np.random.seed(seed + 1)
+    torch.manual_seed(seed + 2)
+    if cuda:
+        torch.cuda.manual_seed_all(seed + 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.05:
+                continue
+            f = [v.strip() for v in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the CPU (reference) path: oracle restatement of the reference, torch fp32, all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(wname: str, steps: int, warmup: int, batch: int, seed: int = 2025):
+    """Times fwd+loss+bwd(+AdamW) of the reference algorithm on the host.  Returns (img/s, seconds, cores, sample)."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import dichavit_oracle as O
+
+    w = WORKLOADS[wname]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oc = O.OracleConfig(pretrained_model_name=w["size"], img_size=w["img"], patch_size=w["patch"],
+                        in_channel_names=[f"c{i}" for i in range(w["channels"])], num_classes=w["classes"],
+                        enable_sample=w["sample"], hcs_sampling="lowest_cosine_prob", hcs_sampling_temp=w["hcs_temp"],
+                        proxy_loss_lambda=w["l_cdl"], ortho_loss_v1_lambda=w["l_tdl"], gamma_s=w["gs"], gamma_d=w["gd"],
+                        reverse_pos_pairs=True, use_square=False)
+    set_seeds(seed, False)
+    weights = O.make_weights(oc, True, seed)
+    params = {k: v.clone().requires_grad_(True) for k, v in weights.items() if k != "adaptive_interface.0"}
+    opt = torch.optim.AdamW([p for p in params.values()], lr=4e-4, weight_decay=0.04)
+    channels = list(range(w["channels"]))
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, w["channels"], w["img"], w["img"], generator=g)
+    y = torch.randint(0, w["classes"], (batch,), generator=g)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        o = O.forward(x, params, oc, channels, training=True, has_head=True)
+        loss = F.cross_entropy(o.out, y) + o.extra_loss * 1.0
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return batch * len(times) / total, total, cores, f"{len(times)} steps of B={batch} (seeded DCS draws), after {warmup} warm-up"
+
+
+def reference_arm(args, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[wname]
+    batch = 4 if w["img"] >= 224 else 32
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    ips, secs, cores, sample = cpu_reference_run(wname, steps, warm, batch)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1000.0 * secs / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "per_gpu_batch": w["batch"], "sample_batch": batch},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_flops_attn(B, L, D, bwd: bool):
+    return (8.0 if bwd else 4.0) * L * L * D * B
+
+
+def ours(args, wname):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    from diverse_channel_vit_b200 import _lib
+    from diverse_channel_vit_b200.dichavit import dichavit
+
+    w = WORKLOADS[wname]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+
+    B = w["batch"]
+    set_seeds(2025, True)
+    model = dichavit(model_cfg(w), mapper={"train": list(range(w["channels"]))}).to(dev)
+    model.train()
+    if world > 1:
+        model.enable_data_parallel()
+    opt = torch.optim.AdamW(model.parameters(), lr=4e-4, weight_decay=0.04, fused=True)
+    gen = torch.Generator(device="cpu").manual_seed(2025 + rank)
+    x_host = torch.randn(B, w["channels"], w["img"], w["img"], generator=gen).pin_memory()
+    y_host = torch.randint(0, w["classes"], (B,), generator=gen).pin_memory()
+    x_dev = x_host.to(dev)
+    y_dev = y_host.to(dev)
+    # > 126 MB L2 flush buffer, written between timed steps is unnecessary here: one step streams several GB
+    # of activations (far larger than L2); stated in config.l2.
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        out, extra = model(x, "train")
+        loss = F.cross_entropy(out, y) + extra * 1.0  # trainer.py:986-995
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e: bool, seed: int):
+        """returns max-over-ranks elapsed ms (CUDA events) and per-step host-visible losses"""
+        random.seed(seed)  # DCS draws: identical on every rank and in every pass
+        torch.manual_seed(seed + 2)
+        torch.cuda.manual_seed_all(seed + 4)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            if e2e:
+                xd = x_host.to(dev, non_blocking=True)
+                yd = y_host.to(dev, non_blocking=True)
+                loss = step(xd, yd)
+                loss.item()  # D2H read of the step's result
+            else:
+                step(x_dev, y_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return ms.item()
+
+    K, W = args.steps, args.warmup
+    timed(max(W, 3), False, 1)  # warm-up (allocator, kernel attributes, NCCL)
+    clk = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    t0 = time.time()
+    ms = timed(K, False, 2025)
+    t1 = time.time()
+    launches = _lib.launch_count() - l0
+    clocks = clk.stop(t0, t1) if clk else None
+    value = world * B * K / (ms / 1000.0)
+
+    timed(2, True, 1)
+    ms_e2e = timed(K, True, 2025)
+    e2e_value = world * B * K / (ms_e2e / 1000.0)
+
+    # full-channel (C' = C, no sampling) reference point
+    model.feature_extractor.patch_embed.enable_sample = False
+    timed(2, False, 1)
+    kf = max(3, K // 2)
+    ms_full = timed(kf, False, 2025)
+    full_value = world * B * kf / (ms_full / 1000.0)
+
+    # ---- per-kernel-class breakdown, live CUDA events (separate pass; rank 0 reports) ----
+    lib = _lib.lib()
+    import ctypes
+
+    ntags = lib.dcv_profile_num_tags()
+    lib.dcv_profile_tag_name.restype = ctypes.c_char_p
+    names = [lib.dcv_profile_tag_name(i).decode() for i in range(ntags)]
+    msb = (ctypes.c_double * ntags)()
+    cnt = (ctypes.c_longlong * ntags)()
+    kp = max(2, min(K, 5))
+    barrier()
+    lib.dcv_profile_start()
+    ms_prof = timed(kp, False, 2025)  # still full channels: L fixed, algorithmic work per launch exact
+    lib.dcv_profile_stop(msb, cnt, ntags)
+    prof = {names[i]: {"ms_per_step": msb[i] / kp, "launches_per_step": cnt[i] / kp} for i in range(ntags) if cnt[i]}
+    model.feature_extractor.patch_embed.enable_sample = w["sample"]
+
+    D = model.dim
+    L = 1 + w["channels"] * (w["img"] // w["patch"]) ** 2
+    depth = len(model.feature_extractor.blocks)
+    top = max(prof.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if prof else None
+    roof = None
+    tensor_classes = {"attn_bwd": algorithmic_flops_attn(B, L, D, True), "attn_fwd": algorithmic_flops_attn(B, L, D, False)}
+    M = B * L
+    gemm_flops_fwd = 2.0 * M * D * (3 * D + D + 4 * D + 4 * D)  # qkv, proj, fc1, fc2 per block
+    tensor_classes["gemm_nt"] = gemm_flops_fwd / 4.0  # per launch average (4 launches / block)
+    tensor_classes["gemm_nn"] = gemm_flops_fwd / 4.0
+    tensor_classes["gemm_tn"] = gemm_flops_fwd / 4.0
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback"
+    if top in tensor_classes:
+        per_launch_ms = prof[top]["ms_per_step"] / prof[top]["launches_per_step"]
+        ach = tensor_classes[top] / (per_launch_ms * 1e-3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": per_launch_ms, "share_of_step": prof[top]["ms_per_step"] / (ms_prof / kp),
+                "note": "full-channel pass (L=%d); algorithmic FLOPs per launch, recompute not counted" % L}
+    elif top is not None:
+        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": float(peaks.get("hbm_gbs", 6650.0)),
+                "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
+    attn_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("attn_fwd", "attn_bwd"))
+    attn_tf = depth * (tensor_classes["attn_fwd"] + tensor_classes["attn_bwd"]) / (attn_ms * 1e-3) / 1e12 if attn_ms else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        bb = 4 if w["img"] >= 224 else 32
+        ips, secs, cores, sample = cpu_reference_run(wname, 2, 1, bb)
+        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    h2d = x_host.numel() * 4 + y_host.numel() * 8
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "step": "zero_grad + fwd + CE/extra loss + bwd (+NCCL grad all-reduce) + fused AdamW",
+                   "dcs": "seeded random C' in 1..C per step (python random seed 2025), same draws on every rank",
+                   "l2": "each step streams >5 GB of activations (>> 126 MB L2); no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "full_channels": {"value": full_value, "unit": UNIT, "ms_per_step": ms_full / kf, "tokens": L,
+                          "model_tflops": None},
+        "roofline": roof,
+        "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+        "attn_tflops": attn_tf, "attn_frac_of_peak": (attn_tf / peak_tf) if attn_tf else None,
+        "cpu_baseline": cpu,
+    }
+    # algorithmic model FLOPs of the full-channel step: fwd = 2 T P^2 D + depth (24 L D^2 + 4 L^2 D) + 2 D cls
+    T = L - 1
+    fwd = 2.0 * T * w["patch"] ** 2 * D + depth * (24.0 * L * D * D + 4.0 * L * L * D) + 2.0 * D * w["classes"]
+    line["full_channels"]["model_tflops"] = 3.0 * fwd * B * world / (ms_full / kf * 1e-3) / 1e12
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="jumpcp", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args, args.workload)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    ours(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "host.h"
 
@@ -20,6 +22,36 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------------
+// profiler
+// ---------------------------------------------------------------------------------------------
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+struct ProfRec {
+  cudaEvent_t a, b;
+  int tag;
+};
+static std::vector<ProfRec> g_prof;
+static const char* kProfNames[PT_COUNT] = {"gemm_nt",  "gemm_nn",   "gemm_tn",    "attn_fwd",   "attn_bwd_prep", "attn_bwd",
+                                           "attn_bwd_fin", "ln_fwd", "ln_bwd",  "colsum",     "cast",          "im2col",
+                                           "embed_gemm", "embed_misc", "tdl",    "cdl",        "embed_bwd",     "small"};
+
+ProfScope::ProfScope(int tag, cudaStream_t s) : slot(-1), st(s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.tag = tag;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+  slot = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot].b, st);
+}
 
 int num_sms() {
   static int sms = 0;
@@ -197,5 +229,40 @@ int dcv_head_bwd(const float* d_out, const float* x_last, int B, int L, int D, c
 }
 
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo_bytes, sbo_bytes); }
+
+int dcv_profile_num_tags(void) { return PT_COUNT; }
+const char* dcv_profile_tag_name(int tag) { return (tag >= 0 && tag < PT_COUNT) ? kProfNames[tag] : ""; }
+
+int dcv_profile_start(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on.store(true);
+  return 0;
+}
+
+int dcv_profile_stop(double* ms_by_tag, long long* launches_by_tag, int ntags) {
+  g_prof_on.store(false);
+  if (cudaDeviceSynchronize() != cudaSuccess) return set_error(DCV_ERR_CUDA, "dcv_profile_stop: device sync failed");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < ntags; ++i) {
+    if (ms_by_tag) ms_by_tag[i] = 0.0;
+    if (launches_by_tag) launches_by_tag[i] = 0;
+  }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.tag < ntags) {
+      if (ms_by_tag) ms_by_tag[r.tag] += ms;
+      if (launches_by_tag) launches_by_tag[r.tag] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 }  // extern "C"

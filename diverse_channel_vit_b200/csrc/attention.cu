@@ -244,6 +244,7 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse2 = lse2;
   dim3 grid((L + kTq - 1) / kTq, H, B);
+  ProfScope prof(PT_ATTN_FWD, st);
   attn_fwd_kernel<<<grid, 192, kFwdSmem, st>>>(map, p);
   DCV_CUDA(cudaGetLastError());
   count_launch();
@@ -635,12 +636,13 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
     attr_done = true;
   }
   {
+    ProfScope prof(PT_ATTN_BWD_PREP, st);
     const long long total = static_cast<long long>(B) * L * H * 8;
     attn_bwd_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(dO), delta, B, L, H, Lp);
     DCV_CUDA(cudaGetLastError());
+    DCV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * H * L * kHd * sizeof(float), st));
   }
-  DCV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * H * L * kHd * sizeof(float), st));
   AttnBwdParams p;
   p.B = B; p.L = L; p.H = H; p.D = D; p.Lp = Lp;
   p.scale = scale;
@@ -648,9 +650,13 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   p.lse2 = lse2; p.delta = delta; p.dq_acc = dq_acc;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   dim3 grid((L + kTk - 1) / kTk, H, B);
-  attn_bwd_kernel<<<grid, 192, kBwdSmem, st>>>(map_qkv, map_do, p);
-  DCV_CUDA(cudaGetLastError());
   {
+    ProfScope prof(PT_ATTN_BWD, st);
+    attn_bwd_kernel<<<grid, 192, kBwdSmem, st>>>(map_qkv, map_do, p);
+    DCV_CUDA(cudaGetLastError());
+  }
+  {
+    ProfScope prof(PT_ATTN_BWD_FIN, st);
     const long long total = static_cast<long long>(B) * H * L * 8;
     attn_bwd_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
         dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H);

@@ -645,6 +645,7 @@ int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, i
                   cudaStream_t st) {
   if (B <= 0 || Cs <= 0 || C <= 0) return set_error(DCV_ERR_INVALID, "im2col: empty problem");
   if (H % P || W % P || P % 4 || W % 4) return set_error(DCV_ERR_UNSUPPORTED, "im2col: H, W multiples of P; P, W of 4");
+  ProfScope prof(PT_IM2COL, st);
   const long long strips = static_cast<long long>(B) * Cs * (H / P);
   im2col_gather_kernel<<<static_cast<unsigned>(strips), 256, 0, st>>>(x, idx, reinterpret_cast<__nv_bfloat16*>(patches),
                                                                         C, Cs, H, W, P);
@@ -656,6 +657,7 @@ int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, i
 int embed_addend(const float* bias, const float* chan_embed, const int* gid, const float* pos_patch, const float* cls,
                  const float* pos0, float* addend, float* tokens, int B, int Cs, int N, int D, cudaStream_t st) {
   if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "embed_addend: D %% 4");
+  ProfScope prof(PT_EMBED_MISC, st);
   const long long total = (static_cast<long long>(Cs) * N + B) * (D / 4);
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
   embed_addend_kernel<<<blocks, 256, 0, st>>>(bias, chan_embed, gid, pos_patch, cls, pos0, addend, tokens, B, Cs, N, D);
@@ -669,6 +671,7 @@ int tdl_fwd(const float* tokens, const float* addend, const float* bias, float* 
             float gamma_s, float gamma_d, int reverse_pos_pairs, int use_square, cudaStream_t st) {
   if (B <= 0 || Cs <= 0 || N <= 0) return set_error(DCV_ERR_INVALID, "tdl_fwd: empty problem");
   if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "tdl_fwd: D %% 4");
+  ProfScope prof(PT_TDL, st);
   const size_t smem = (static_cast<size_t>(kTdlWarps) * D + kTdlWarps) * sizeof(float);
   DCV_NV_SWITCH(D, tdl_sum_kernel<NV><<<B * Cs, kTdlWarps * 32, smem, st>>>(tokens, addend, bias, S, Q, rnorm, Cs, N, D));
   DCV_CUDA(cudaGetLastError());
@@ -685,6 +688,7 @@ int embed_bwd_dy(const float* G, const float* tokens, const float* addend, const
                  const float* S, const float* S_all, const float* coef_pos, const float* coef_neg,
                  const float* d_extra, float lambda_tdl, void* dY, int B, int Cs, int N, int D, cudaStream_t st) {
   if (B <= 0 || Cs <= 0 || N <= 0) return set_error(DCV_ERR_INVALID, "embed_bwd_dy: empty problem");
+  ProfScope prof(PT_EMBED_BWD, st);
   const long long rows = static_cast<long long>(B) * Cs * N;
   const int blocks = static_cast<int>(std::min<long long>((rows + 7) / 8, 148 * 16));
   DCV_NV_SWITCH(D, embed_bwd_dy_kernel<NV><<<blocks, 256, 0, st>>>(G, tokens, addend, bias, rnorm, S, S_all, coef_pos,
@@ -697,6 +701,7 @@ int embed_bwd_dy(const float* G, const float* tokens, const float* addend, const
 
 int embed_param_grads(const float* G, float* R, const int* gid, float* d_cls, float* d_pos0, float* d_chan_embed,
                       float* dpos_patch, int accumulate_pos, int B, int Cs, int N, int D, cudaStream_t st) {
+  ProfScope prof(PT_EMBED_BWD, st);
   const long long L = static_cast<long long>(Cs) * N + 1;
   const long long LD4 = L * (D / 4);
   batch_sum_kernel<<<static_cast<unsigned>((LD4 + 255) / 256), 256, 0, st>>>(G, R, B, LD4);
@@ -711,6 +716,7 @@ int embed_param_grads(const float* G, float* R, const int* gid, float* d_cls, fl
 int cdl_fwd(const float* chan_embed, const float* proxies, const int* gid, float scale, float* loss, float* dE,
             float* dP, int Cs, int D, cudaStream_t st) {
   if (Cs <= 0 || Cs > kCdlMaxC) return set_error(DCV_ERR_UNSUPPORTED, "cdl_fwd: C'=%d must be in [1,%d]", Cs, kCdlMaxC);
+  ProfScope prof(PT_CDL, st);
   const size_t smem = static_cast<size_t>(2) * Cs * D * sizeof(float);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
@@ -726,6 +732,7 @@ int cdl_fwd(const float* chan_embed, const float* proxies, const int* gid, float
 
 int cdl_bwd(const float* dE, const float* dP, const int* gid, const float* d_extra, float lambda_cdl,
             float* g_chan_embed, float* g_proxies, int Cs, int D, cudaStream_t st) {
+  ProfScope prof(PT_CDL, st);
   cdl_bwd_kernel<<<(Cs * D + 255) / 256, 256, 0, st>>>(dE, dP, gid, d_extra, lambda_cdl, g_chan_embed, g_proxies, Cs, D);
   DCV_CUDA(cudaGetLastError());
   count_launch();
@@ -733,6 +740,7 @@ int cdl_bwd(const float* dE, const float* dP, const int* gid, const float* d_ext
 }
 
 int extra_loss(const float* tdl, const float* cdl, float lt, float lc, float* extra, cudaStream_t st) {
+  ProfScope prof(PT_EMBED_MISC, st);
   extra_loss_kernel<<<1, 1, 0, st>>>(tdl, cdl, lt, lc, extra);
   DCV_CUDA(cudaGetLastError());
   count_launch();
@@ -742,6 +750,7 @@ int extra_loss(const float* tdl, const float* cdl, float lt, float lc, float* ex
 int sgemm_small(const float* A, int lda, int transA, const float* Bm, int ldb, int transB, float* C, int ldc,
                 const float* bias, int accumulate, int M, int N, int K, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(DCV_ERR_INVALID, "sgemm_small: empty problem");
+  ProfScope prof(PT_SMALL, st);
   dim3 grid((N + 31) / 32, (M + 31) / 32);
   sgemm_small_kernel<<<grid, 256, 0, st>>>(A, lda, transA, Bm, ldb, transB, C, ldc, bias, accumulate, M, N, K);
   DCV_CUDA(cudaGetLastError());
@@ -752,6 +761,7 @@ int sgemm_small(const float* A, int lda, int transA, const float* Bm, int ldb, i
 int cls_ln_fwd(const float* x, long long row_stride, const float* gamma, const float* beta, float* feat, float* mean,
                float* rstd, int B, int D, float eps, cudaStream_t st) {
   if (B <= 0) return set_error(DCV_ERR_INVALID, "cls_ln_fwd: empty");
+  ProfScope prof(PT_SMALL, st);
   DCV_NV_SWITCH(D, cls_ln_fwd_kernel<NV><<<(B + 3) / 4, 128, 0, st>>>(x, row_stride, gamma, beta, feat, mean, rstd, B, D, eps));
   DCV_CUDA(cudaGetLastError());
   count_launch();
@@ -762,6 +772,7 @@ int cls_ln_bwd(const float* dfeat, const float* x, long long row_stride, const f
                const float* gamma, float* dres, void* dres_bf16, float* dgamma, float* dbeta, float* dxsum, int B,
                int D, cudaStream_t st) {
   if (B <= 0) return set_error(DCV_ERR_INVALID, "cls_ln_bwd: empty");
+  ProfScope prof(PT_SMALL, st);
   DCV_NV_SWITCH(D, cls_ln_bwd_kernel<NV><<<(B + 3) / 4, 128, 0, st>>>(dfeat, x, row_stride, mean, rstd, gamma, dres,
                                                                       reinterpret_cast<__nv_bfloat16*>(dres_bf16),
                                                                       dgamma, dbeta, dxsum, B, D));

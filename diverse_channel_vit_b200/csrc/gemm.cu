@@ -464,6 +464,7 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   else if (N % 128 == 0) bn = 128;
   else if (N % 64 == 0) bn = 64;
   else return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: N=%d must be a multiple of 64", N);
+  ProfScope prof(b_mn ? PT_GEMM_NN : (epi == EPI_EMBED ? PT_EMBED_GEMM : PT_GEMM_NT), st);
   CUtensorMap ma, mb;
   if (int e = make_tmap_bf16_2d(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM)) return e;
   if (b_mn) {
@@ -528,6 +529,7 @@ int gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int
   else if (Kout % 128 == 0) bn = 128;
   else if (Kout % 64 == 0) bn = 64;
   else return set_error(DCV_ERR_UNSUPPORTED, "gemm_tn: Kout=%d must be a multiple of 64", Kout);
+  ProfScope prof(PT_GEMM_TN, st);
   CUtensorMap ma, mb;
   if (int e = make_tmap_bf16_2d(&ma, A, (uint64_t)Nout, (uint64_t)M, (uint64_t)lda * 2, 64, kBK)) return e;
   if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)Kout, (uint64_t)M, (uint64_t)ldb * 2, 64, kBK)) return e;

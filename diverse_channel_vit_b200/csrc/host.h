@@ -20,6 +20,36 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
 int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 
+// ---- built-in kernel profiler (api.cu): CUDA-event pairs around every launch of a tagged kernel
+// class, recorded on the launching stream; off by default (one predictable branch per launch).
+enum ProfTag {
+  PT_GEMM_NT = 0,    // forward Linear (bias / gelu / residual epilogues)
+  PT_GEMM_NN,        // dgrad
+  PT_GEMM_TN,        // wgrad (split-K)
+  PT_ATTN_FWD,
+  PT_ATTN_BWD_PREP,  // delta = rowsum(dO o O) + dq accumulator clear
+  PT_ATTN_BWD,
+  PT_ATTN_BWD_FIN,   // fp32 dq accumulator -> bf16
+  PT_LN_FWD,
+  PT_LN_BWD,
+  PT_COLSUM,
+  PT_CAST,
+  PT_IM2COL,
+  PT_EMBED_GEMM,
+  PT_EMBED_MISC,     // addend / CLS rows / extra-loss scalar
+  PT_TDL,
+  PT_CDL,
+  PT_EMBED_BWD,      // dY assembly, batch sums, cls/pos/channel-token gradients
+  PT_SMALL,          // fp32 SIMT GEMM (pos resample, head), CLS LayerNorm
+  PT_COUNT
+};
+struct ProfScope {
+  ProfScope(int tag, cudaStream_t st);
+  ~ProfScope();
+  int slot;
+  cudaStream_t st;
+};
+
 #define DCV_CUDA(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \

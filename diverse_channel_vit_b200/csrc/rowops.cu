@@ -237,6 +237,7 @@ int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float
            float eps, cudaStream_t st) {
   if (M <= 0 || D <= 0) return set_error(DCV_ERR_INVALID, "ln_fwd: empty problem");
   if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "ln_fwd: D=%d must be a multiple of 4", D);
+  ProfScope prof(PT_LN_FWD, st);
   const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 8);
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   switch (nv_for(D)) {
@@ -255,6 +256,7 @@ int ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd,
            void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int M, int D, cudaStream_t st) {
   if (M <= 0 || D <= 0) return set_error(DCV_ERR_INVALID, "ln_bwd: empty problem");
   if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "ln_bwd: D=%d must be a multiple of 4", D);
+  ProfScope prof(PT_LN_BWD, st);
   const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 2);
   const size_t smem = static_cast<size_t>(kRowWarps) * D * sizeof(float);
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
@@ -278,6 +280,7 @@ int ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd,
 int colsum_bf16(const void* a, float* out, int M, int N, int lda, cudaStream_t st) {
   if (M <= 0 || N <= 0) return set_error(DCV_ERR_INVALID, "colsum: empty problem");
   if (N % 8 || lda % 8) return set_error(DCV_ERR_UNSUPPORTED, "colsum: N and lda must be multiples of 8");
+  ProfScope prof(PT_COLSUM, st);
   const int cb = (N + 255) / 256;
   int splits = (num_sms() * 4 + cb - 1) / cb;
   if (splits > (M + 31) / 32) splits = (M + 31) / 32;
@@ -291,6 +294,7 @@ int colsum_bf16(const void* a, float* out, int M, int N, int lda, cudaStream_t s
 
 int colsum_f32(const float* a, float* out, int M, int N, int lda, cudaStream_t st) {
   if (M <= 0 || N <= 0) return set_error(DCV_ERR_INVALID, "colsum_f32: empty problem");
+  ProfScope prof(PT_SMALL, st);
   colsum_f32_kernel<<<(N + 127) / 128, 128, 0, st>>>(a, out, M, N, lda);
   DCV_CUDA(cudaGetLastError());
   count_launch();
@@ -299,6 +303,7 @@ int colsum_f32(const float* a, float* out, int M, int N, int lda, cudaStream_t s
 
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
   if (n <= 0) return set_error(DCV_ERR_INVALID, "cast: empty");
+  ProfScope prof(PT_CAST, st);
   const long long threads = (n + 3) / 4;
   cast_f32_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);

@@ -223,6 +223,14 @@ int dcv_head_bwd(const float* d_out, const float* x_last, int B, int L, int D, c
                  float* dfeat_ws, float* dres, void* dres_bf16, float* g_norm_w, float* g_norm_b, float* g_head_w,
                  float* g_head_b, float* dbias_last, void* stream);
 
+/* ---- built-in profiler: CUDA-event pairs around every kernel launch of each kernel class, on the
+ * launching stream.  start() arms it; stop() synchronises the device (profiling only -- never on the
+ * training path) and returns total milliseconds and scope counts per class. ---- */
+int dcv_profile_num_tags(void);
+const char* dcv_profile_tag_name(int tag);
+int dcv_profile_start(void);
+int dcv_profile_stop(double* ms_by_tag, long long* launches_by_tag, int ntags);
+
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);
 
