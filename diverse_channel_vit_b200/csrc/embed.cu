@@ -13,9 +13,13 @@
 namespace dcv {
 
 // ---------------------------------------------------------------------------------
-// DCS gather + im2col: x fp32 [B, C, H, W], idx int32 [C'] -> patches bf16 [B*C'*N, P*P]
+// DCS gather + im2col: x fp32 [B, C, H, W], idx int32 [C'] -> patches bf16 [B*C'*N, 3*P*P]
 // (row = (b, c', hp, wp), column k = ph * P + pw).   reference dichavit.py:210 (x[:, idx]) and
 // the unfold implied by Conv3d(1, D, (1,P,P), stride (1,P,P)) at :77-82,377.
+// Each fp32 pixel is split into two bf16 (x = hi + lo, 16 mantissa bits kept); a row holds
+// [hi | lo | hi] so that ONE bf16 GEMM against the split weight [Whi | Whi | Wlo] (below) yields
+// hi*Whi + lo*Whi + hi*Wlo = x*W to ~2^-16: the reference projects in fp32 and the TDL scalar
+// (tolerance 1e-3) is a difference of large sums of these outputs.
 // One CTA per (b, c', hp) strip of P image rows: reads are full 128-byte lines along W,
 // writes are 8-byte pieces that fill whole 32-byte sectors.
 // ---------------------------------------------------------------------------------
@@ -30,18 +34,39 @@ im2col_gather_kernel(const float* __restrict__ x, const int* __restrict__ idx, _
   const int b = strip / Cs;
   const int c_src = idx ? __ldg(idx + cs) : cs;
   const float* src = x + ((static_cast<size_t>(b) * C + c_src) * H + static_cast<size_t>(hp) * P) * W;
-  __nv_bfloat16* dst = patches + ((static_cast<size_t>(b) * Cs + cs) * hp_count + hp) * wp_count * (P * P);
+  const int KK = P * P;
+  __nv_bfloat16* dst = patches + ((static_cast<size_t>(b) * Cs + cs) * hp_count + hp) * wp_count * (3 * KK);
   const int w4 = W >> 2;
   for (int i = threadIdx.x; i < P * w4; i += blockDim.x) {
     const int ph = i / w4, wq = i - ph * w4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(ph) * W) + wq);
     const int w = wq * 4;
     const int wp = w / P, pw = w - wp * P;
-    uint2 o;
-    o.x = pack_bf16(v.x, v.y);
-    o.y = pack_bf16(v.z, v.w);
-    *reinterpret_cast<uint2*>(dst + static_cast<size_t>(wp) * (P * P) + ph * P + pw) = o;
+    uint2 hi, lo;
+    hi.x = pack_bf16(v.x, v.y);
+    hi.y = pack_bf16(v.z, v.w);
+    const float2 h01 = unpack_bf16(hi.x), h23 = unpack_bf16(hi.y);
+    lo.x = pack_bf16(v.x - h01.x, v.y - h01.y);
+    lo.y = pack_bf16(v.z - h23.x, v.w - h23.y);
+    __nv_bfloat16* row = dst + static_cast<size_t>(wp) * (3 * KK) + ph * P + pw;
+    *reinterpret_cast<uint2*>(row) = hi;
+    *reinterpret_cast<uint2*>(row + KK) = lo;
+    *reinterpret_cast<uint2*>(row + 2 * KK) = hi;
   }
+}
+
+// conv weight fp32 [D, K] -> bf16 [D, 3K] = [Whi | Whi | Wlo]  (see im2col_gather_kernel)
+__global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws, int D, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D * K) return;
+  const int d = i / K, k = i - d * K;
+  const float v = w[i];
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+  __nv_bfloat16* row = ws + static_cast<size_t>(d) * (3 * K);
+  row[k] = hi;
+  row[K + k] = hi;
+  row[2 * K + k] = lo;
 }
 
 // ---------------------------------------------------------------------------------
@@ -649,6 +674,14 @@ int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, i
   const long long strips = static_cast<long long>(B) * Cs * (H / P);
   im2col_gather_kernel<<<static_cast<unsigned>(strips), 256, 0, st>>>(x, idx, reinterpret_cast<__nv_bfloat16*>(patches),
                                                                         C, Cs, H, W, P);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int split_weight(const float* w, void* ws, int D, int K, cudaStream_t st) {
+  ProfScope prof(PT_EMBED_MISC, st);
+  split_weight_kernel<<<(D * K + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(ws), D, K);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -83,6 +83,7 @@ int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st);
 // ---- embed.cu ----
 int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, int Cs, int H, int W, int P,
                   cudaStream_t st);
+int split_weight(const float* w, void* ws, int D, int K, cudaStream_t st);
 int embed_addend(const float* bias, const float* chan_embed, const int* gid, const float* pos_patch, const float* cls,
                  const float* pos0, float* addend, float* tokens, int B, int Cs, int N, int D, cudaStream_t st);
 int tdl_fwd(const float* tokens, const float* addend, const float* bias, float* S, float* Q, float* rnorm,

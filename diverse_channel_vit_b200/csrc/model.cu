@@ -76,10 +76,12 @@ static int check_embed(const dcv_embed_dims& d) {
 int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const float* x,
               const int* idx, const int* gid, const dcv_embed_acts& a, cudaStream_t st) {
   DCV_TRY(check_embed(d));
-  if (!x || !gid || !a.patches || !a.addend || !a.tokens || !a.extra) return set_error(DCV_ERR_INVALID, "embed_fwd: null pointer");
+  if (!x || !gid || !a.patches || !a.wsplit || !a.addend || !a.tokens || !a.extra)
+    return set_error(DCV_ERR_INVALID, "embed_fwd: null pointer");
   const int N = (d.H / d.P) * (d.W / d.P), T = d.Cs * N, K = d.P * d.P, D = d.D;
   // DCS gather + unfold (dichavit.py:210, :377)
   DCV_TRY(im2col_gather(x, idx, a.patches, d.B, d.C, d.Cs, d.H, d.W, d.P, st));
+  DCV_TRY(split_weight(p.proj_w, a.wsplit, D, K, st));
   // positional embedding of the patches: raw or bicubic-resampled (dichavit.py:529-552)
   const float* pos_patch = p.pos + D;
   if (p.pos_map) {
@@ -88,8 +90,9 @@ int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed
   }
   DCV_TRY(embed_addend(p.proj_b, p.chan_embed, gid, pos_patch, p.cls, p.pos, a.addend, a.tokens, d.B, d.Cs, N, D, st));
   // tokens[b, 1 + t, :] = patches * W^T + addend[t]   (conv + bias + channel token + pos, :377,:409-411,:565)
-  DCV_TRY(gemm_nt(a.patches, K, p.proj_w, K, d.B * T, D, K, EPI_EMBED, nullptr, a.tokens, nullptr, nullptr, nullptr, D,
-                  false, st, T, T + 1, a.addend));
+  // (3K-wide split-precision operands: [hi|lo|hi] x [Whi|Whi|Wlo]^T, fp32 accumulation in TMEM)
+  DCV_TRY(gemm_nt(a.patches, 3 * K, a.wsplit, 3 * K, d.B * T, D, 3 * K, EPI_EMBED, nullptr, a.tokens, nullptr, nullptr,
+                  nullptr, D, false, st, T, T + 1, a.addend));
   const bool tdl_on = cfg.lambda_tdl > 0.f, cdl_on = cfg.lambda_cdl > 0.f;
   if (tdl_on)
     DCV_TRY(tdl_fwd(a.tokens, a.addend, p.proj_b, a.S, a.Q, a.rnorm, a.S_all, a.loss_b, a.coef_pos, a.coef_neg, a.tdl,
@@ -113,7 +116,7 @@ int embed_bwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed
   DCV_TRY(embed_bwd_dy(G, a.tokens, a.addend, p.proj_b, a.rnorm, tdl_on ? a.S : nullptr, a.S_all, a.coef_pos, a.coef_neg,
                        d_extra, tdl_on ? cfg.lambda_tdl : 0.f, ws.dY, d.B, d.Cs, N, D, st));
   // conv weight / bias gradients: dW[D, P*P] += dY^T patches ; db += colsum(dY)
-  DCV_TRY(gemm_tn(ws.dY, D, a.patches, K, M, D, K, g.proj_w, K, 1, 0, st));
+  DCV_TRY(gemm_tn(ws.dY, D, a.patches, 3 * K, M, D, K, g.proj_w, K, 1, 0, st));  // hi part of the patches
   DCV_TRY(colsum_bf16(ws.dY, g.proj_b, M, D, D, st));
   // cls / pos / channel-token gradients from the batch-summed token gradient
   float* pos_patch_grad = p.pos_map ? ws.dpos_patch : g.pos + D;

@@ -83,7 +83,7 @@ class _EmbedGrads(Structure):
 
 
 class _EmbedActs(Structure):
-    _fields_ = [(n, c_void_p) for n in ("patches", "pos_patch", "addend", "tokens", "S", "Q", "rnorm", "S_all",
+    _fields_ = [(n, c_void_p) for n in ("patches", "wsplit", "pos_patch", "addend", "tokens", "S", "Q", "rnorm", "S_all",
                                         "loss_b", "coef_pos", "coef_neg", "cdl_dE", "cdl_dP", "tdl", "cdl", "extra")]
 
 
@@ -505,7 +505,8 @@ class DiChaViT(nn.Module):
         Lp = _round_up(L, 128)
         depth = len(fe.blocks)
         ar = _Arena()
-        ar.add("patches", B * T * P * P * 2)
+        ar.add("patches", B * T * 3 * P * P * 2)
+        ar.add("wsplit", D * 3 * P * P * 2)
         ar.add("pos_patch", N * D * 4)
         ar.add("addend", T * D * 4)
         for nm, sz in (("S", B * cs * D), ("Q", B * cs), ("rnorm", B * T), ("S_all", B * D), ("loss_b", B),
@@ -544,11 +545,11 @@ class DiChaViT(nn.Module):
                          int(bool(cfg.use_square)))
         has_prox = hasattr(pe, "channel_emb_proxies")
         pos_map = self._pos_map(pl["W"], pl["H"], device) if use_map else None
-        ep = _EmbedParams(self._bptr(pe.proj.weight), self._fptr(pe.proj.bias), self._fptr(pe.channel_embed.weight),
+        ep = _EmbedParams(self._fptr(pe.proj.weight), self._fptr(pe.proj.bias), self._fptr(pe.channel_embed.weight),
                           self._fptr(pe.channel_emb_proxies) if has_prox else None, self._fptr(fe.cls_token),
                           self._fptr(fe.pos_embed), pos_map.data_ptr() if pos_map is not None else None)
         sp = scal.data_ptr()
-        acts = _EmbedActs(base + s["patches"], base + s["pos_patch"], base + s["addend"], base + s["x0"],
+        acts = _EmbedActs(base + s["patches"], base + s["wsplit"], base + s["pos_patch"], base + s["addend"], base + s["x0"],
                           base + s["S"], base + s["Q"], base + s["rnorm"], base + s["S_all"], base + s["loss_b"],
                           base + s["coef_pos"], base + s["coef_neg"], base + s["cdl_dE"], base + s["cdl_dP"],
                           sp, sp + 4, sp + 8)

@@ -108,3 +108,50 @@ def attn_bwd(qkv, o, do, lse2, B, L, H, scale=None, dqkv=None, delta=None, dq_ac
     check(_lib.lib().dcv_attn_bwd(ptr(qkv), ptr(o), ptr(do), ptr(lse2), ptr(delta), ptr(dq_acc), ptr(dqkv), B, L, H,
                                   ctypes.c_float(scale), stream_ptr()), "dcv_attn_bwd")
     return dqkv
+
+
+def ln_fwd(x, gamma, beta, eps=1e-6):
+    """x fp32 [M,D] -> (y bf16, mean, rstd)."""
+    _req(x, torch.float32, "x")
+    M, D = x.shape
+    y = torch.empty((M, D), device=x.device, dtype=torch.bfloat16)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    check(_lib.lib().dcv_ln_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, ctypes.c_float(eps),
+                                stream_ptr()), "dcv_ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta, dxsum=None):
+    """dres (fp32, in place) += LN'(dy); returns the bf16 copy of the updated dres."""
+    _req(dy, torch.bfloat16, "dy"); _req(x, torch.float32, "x"); _req(dres, torch.float32, "dres")
+    M, D = x.shape
+    dxb = torch.empty((M, D), device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().dcv_ln_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dxb), ptr(dgamma),
+                                ptr(dbeta), ptr(dxsum), M, D, stream_ptr()), "dcv_ln_bwd")
+    return dxb
+
+
+def colsum_bf16(a, out):
+    _req(a, torch.bfloat16, "a")
+    check(_lib.lib().dcv_colsum_bf16(ptr(a), ptr(out), a.shape[0], a.shape[1], a.stride(0), stream_ptr()), "dcv_colsum_bf16")
+    return out
+
+
+def cast_f32_bf16(src):
+    _req(src, torch.float32, "src")
+    dst = torch.empty_like(src, dtype=torch.bfloat16)
+    check(_lib.lib().dcv_cast_f32_bf16(ptr(src), ptr(dst), ctypes.c_longlong(src.numel()), stream_ptr()), "dcv_cast_f32_bf16")
+    return dst
+
+
+def sgemm_small(a, b, bias=None, out=None, accumulate=False, trans_a=False, trans_b=False):
+    """fp32 C = op(a) op(b) (+bias); trans_a: a stored [K,M]; trans_b: b stored [N,K]."""
+    _req(a, torch.float32, "a"); _req(b, torch.float32, "b")
+    M, Kd = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    if out is None:
+        out = torch.zeros((M, N), device=a.device, dtype=torch.float32)
+    check(_lib.lib().dcv_sgemm_small(ptr(a), a.stride(0), int(trans_a), ptr(b), b.stride(0), int(trans_b), ptr(out),
+                                     out.stride(0), ptr(bias), int(accumulate), M, N, Kd, stream_ptr()), "dcv_sgemm_small")
+    return out

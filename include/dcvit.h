@@ -170,7 +170,7 @@ typedef struct dcv_embed_cfg {
 } dcv_embed_cfg;
 
 typedef struct dcv_embed_params {
-  const void* proj_w;      /* bf16 [D, P*P] (Conv3d weight reshaped)                       */
+  const float* proj_w;     /* fp32 [D, P*P] (Conv3d weight reshaped)                       */
   const float* proj_b;     /* [D]                                                          */
   const float* chan_embed; /* [C_total, D] channel_embed.weight                            */
   const float* proxies;    /* [C_total, D] channel_emb_proxies (NULL if CDL off)           */
@@ -184,7 +184,8 @@ typedef struct dcv_embed_grads { /* fp32, accumulated */
 } dcv_embed_grads;
 
 typedef struct dcv_embed_acts {
-  void* patches;    /* bf16 [B*C'*N, P*P]  gathered im2col rows (A of the GEMM, B of its wgrad) */
+  void* patches;    /* bf16 [B*C'*N, 3*P*P] gathered im2col rows, split precision [hi | lo | hi]  */
+  void* wsplit;     /* bf16 [D, 3*P*P] split conv weight [Whi | Whi | Wlo]                        */
   float* pos_patch; /* fp32 [N, D]   */
   float* addend;    /* fp32 [C'*N, D] bias + channel token + positional embedding            */
   float* tokens;    /* fp32 [B, L, D] output                                                 */

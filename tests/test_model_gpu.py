@@ -1,0 +1,189 @@
+"""GPU: the drop-in DiChaViT module (CUDA kernels through the C ABI) against the CPU oracle on the same seeded
+inputs and weights, and against the golden vectors produced by the unmodified reference.
+
+Tolerances (north_star): bf16 compute -> rel-L2 <= 1e-2 on activations / logits, <= 1e-3 on the CDL / TDL scalars.
+Gradients are compared in rel-L2 per parameter with 3e-2 (bf16 gradient noise accumulates over 12 blocks; the
+positional-embedding gradient is a sum over batch x channels of nearly cancelling terms and is the noisiest)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import (CHAMMI_MAPPER, O, build_cuda_model, cases, cuda_step, load_golden, make_inputs, ref_cfg,
+                        rel_l2)
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-2
+LOSS_TOL = 1e-3
+GRAD_TOL = 3e-2
+
+
+def _oracle(name, indices=None):
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()[name]
+    weights = O.make_weights(oc, has_head, wseed)
+    x, y = make_inputs(oc, B, len(mapper[chunk]), oc.num_classes, iseed)
+    loss, o, grads = O.loss_and_grads(x, y, weights, oc, mapper[chunk], has_head, indices=indices, extra_loss_lambda=xlam)
+    return (oc, mapper, chunk, has_head, xlam, weights, x, y), loss, o, grads
+
+
+def _check_step(name, indices=None, golden=True):
+    (oc, mapper, chunk, has_head, xlam, weights, x, y), o_loss, o, o_grads = _oracle(name, indices)
+    model = build_cuda_model(oc, mapper, weights)
+    out, extra, loss, grads = cuda_step(model, x.cuda(), y.cuda(), chunk, has_head, xlam, indices=indices)
+    torch.cuda.synchronize()
+    assert out.shape == o.out.shape and extra.dim() == 0
+    assert rel_l2(out, o.out) < ACT_TOL
+    ll = model.last_losses
+    if oc.ortho_loss_v1_lambda > 0:
+        assert abs(ll["tdl"].item() - o.tdl.item()) <= LOSS_TOL * abs(o.tdl.item())
+    if oc.proxy_loss_lambda > 0:
+        assert abs(ll["cdl"].item() - o.cdl.item()) <= LOSS_TOL * abs(o.cdl.item())
+    assert abs(extra.item() - o.extra_loss.item()) <= LOSS_TOL * abs(o.extra_loss.item()) + 1e-7
+    for k, g in o_grads.items():
+        cg = grads[k]
+        if g is None or g.abs().max() == 0:
+            assert cg is None or cg.abs().max().item() == 0, k
+            continue
+        assert cg is not None, k
+        assert rel_l2(cg, g) < GRAD_TOL, (k, rel_l2(cg, g))
+    if golden and indices is None:
+        g = load_golden(name)
+        assert rel_l2(out, torch.from_numpy(g["out"])) < ACT_TOL
+        assert abs(extra.item() - float(g["extra"])) <= LOSS_TOL * abs(float(g["extra"])) + 1e-7
+        for k in g.files:
+            if k.startswith("gstat:"):
+                p = k[len("gstat:"):]
+                assert abs(grads[p].double().norm().item() - g[k][0]) <= GRAD_TOL * g[k][0] + 1e-9, p
+    return model
+
+
+@pytest.mark.parametrize("name", [n for n in cases() if n.startswith("tiny")])
+def test_training_step_matches_oracle_and_reference_golden(name):
+    _check_step(name)
+
+
+def test_training_step_vit_small_c1():
+    """BASELINE.json configs[0]: ViT-S/16, batch 8, 3-channel 224x224 (CHAMMI WTC shape), all losses on."""
+    _check_step("small_c1")
+
+
+@pytest.mark.parametrize("indices", [[2], [3, 0], [1, 3, 2], [2, 0, 3, 1]])
+def test_sampled_channel_subsets_in_sampled_order(indices):
+    """DCS gather: token layout follows the SAMPLED order; C'=1 uses the raw positional embedding, C'>1 the bicubic
+    resample; channel tokens / anchors of unsampled channels get exactly zero gradient."""
+    model = _check_step("tiny_chammi_hpa", indices=indices, golden=False)
+    ce = model.feature_extractor.patch_embed.channel_embed.weight.grad
+    sampled = {CHAMMI_MAPPER["HPA"][i] for i in indices}
+    for c in range(12):
+        if c not in sampled:
+            assert ce[c].abs().max().item() == 0
+
+
+def test_dcs_indices_bit_exact_with_oracle_on_device():
+    """Same RNG state (python random + CUDA generator) -> same (C', indices) as the reference algorithm executed on
+    the same device, for all three published temperatures."""
+    oc, mapper, chunk, has_head, *_ = cases()["tiny_chammi_hpa"]
+    for temp in (0.1, 1000.0, 0.01):
+        cfg = ref_cfg(oc)
+        cfg["enable_sample"] = True
+        cfg["hcs_sampling"] = "lowest_cosine_prob"
+        cfg["hcs_sampling_temp"] = temp
+        from diverse_channel_vit_b200.dichavit import dichavit
+
+        m = dichavit(cfg, mapper=mapper).cuda().train()
+        pe = m.feature_extractor.patch_embed
+        for chunk_name, chans in mapper.items():
+            for seed in range(25):
+                random.seed(seed); torch.manual_seed(seed + 2); torch.cuda.manual_seed_all(seed + 4)
+                c_new, idx, gid = pe.select_channels(chunk_name, len(chans), torch.device("cuda"))
+                random.seed(seed); torch.manual_seed(seed + 2); torch.cuda.manual_seed_all(seed + 4)
+                want = O.dcs_select(pe.channel_embed.weight[torch.tensor(chans, device="cuda")].detach(), temp)
+                assert (c_new, idx.tolist()) == (want[0], want[2])
+                assert gid.tolist() == [chans[i] for i in want[2]]
+        assert sum(pe.counter.values()) > 0
+
+
+def test_sampling_forward_end_to_end():
+    """enable_sample=True in train mode: the module samples, gathers and trains without host sync; eval mode uses
+    all channels and returns a bare tensor."""
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["tiny_jumpcp"]
+    cfg = ref_cfg(oc)
+    cfg["enable_sample"] = True
+    cfg["hcs_sampling"] = "lowest_cosine_prob"
+    from diverse_channel_vit_b200.dichavit import dichavit
+
+    weights = O.make_weights(oc, has_head, wseed)
+    m = dichavit(cfg, mapper=mapper)
+    m.load_state_dict({k: weights[k] for k in m.state_dict()})
+    m = m.cuda().train()
+    x, y = make_inputs(oc, B, 8, oc.num_classes, iseed)
+    for seed in (0, 1, 2, 3):
+        random.seed(seed); torch.manual_seed(seed + 2); torch.cuda.manual_seed_all(seed + 4)
+        out, extra = m(x.cuda(), chunk)
+        random.seed(seed); torch.manual_seed(seed + 2); torch.cuda.manual_seed_all(seed + 4)
+        emb = m.feature_extractor.patch_embed.channel_embed.weight.detach()
+        _, _, idx = O.dcs_select(emb, cfg.hcs_sampling_temp)
+        oo = O.forward(x, weights, oc, mapper[chunk], training=True, has_head=has_head, indices=idx)
+        assert rel_l2(out, oo.out) < ACT_TOL
+        assert abs(extra.item() - oo.extra_loss.item()) <= LOSS_TOL * abs(oo.extra_loss.item())
+        (out.sum() + extra).backward()
+    m.eval()
+    with torch.no_grad():
+        out = m(x.cuda(), chunk)
+    assert isinstance(out, torch.Tensor)
+    oe = O.forward(x, weights, oc, mapper[chunk], training=False, has_head=has_head)
+    assert rel_l2(out, oe.out) < ACT_TOL
+
+
+def test_state_dict_roundtrip_and_optimizer_step():
+    """Parameters are views of one flat buffer: load_state_dict / optimizer updates must be seen by the kernels."""
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["tiny_jumpcp"]
+    weights = O.make_weights(oc, has_head, wseed)
+    m = build_cuda_model(oc, mapper, weights)
+    x, y = make_inputs(oc, B, 8, oc.num_classes, iseed)
+    out1, _, _, _ = cuda_step(m, x.cuda(), y.cuda(), chunk, has_head, xlam)
+    w2 = O.make_weights(oc, has_head, wseed + 1)
+    m.load_state_dict({k: w2[k] for k in m.state_dict()})
+    out2, _, _, grads = cuda_step(m, x.cuda(), y.cuda(), chunk, has_head, xlam)
+    o2 = O.forward(x, w2, oc, mapper[chunk], training=True, has_head=has_head)
+    assert rel_l2(out2, o2.out) < ACT_TOL and rel_l2(out1, o2.out) > 0.1
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    opt.step()
+    w3 = {k: (v - 0.5 * grads[k].cpu() if k in grads and grads[k] is not None else v) for k, v in w2.items()}
+    w3["adaptive_interface.0"] = w3["proxies"]
+    m.eval()
+    with torch.no_grad():
+        out3 = m(x.cuda(), chunk)
+    o3 = O.forward(x, w3, oc, mapper[chunk], training=False, has_head=has_head)
+    assert rel_l2(out3, o3.out) < 2e-2
+
+
+def test_full_size_properties_jumpcp():
+    """BASELINE configs[2] shape (ViT-S/16, 8 channels 224x224, L=1569) where the oracle is too slow: properties.
+    (1) batch independence: images are processed independently -> a permuted batch gives permuted logits;
+    (2) channel-order equivariance of the token set: permuting the input channels together with the mapper leaves
+        the logits unchanged up to bf16 noise; (3) finite gradients for every parameter."""
+    from tests.util import Cfg
+    from diverse_channel_vit_b200.dichavit import dichavit
+    import bench
+
+    w = bench.WORKLOADS["jumpcp"]
+    cfg = bench.model_cfg(w)
+    cfg["enable_sample"] = False
+    torch.manual_seed(0)
+    m = dichavit(cfg, mapper={"train": list(range(8)), "perm": [3, 1, 7, 0, 2, 6, 5, 4]}).cuda().train()
+    x = torch.randn(6, 8, 224, 224, device="cuda")
+    out, extra = m(x, "train")
+    perm = torch.tensor([4, 2, 0, 5, 1, 3], device="cuda")
+    out_p, extra_p = m(x[perm], "train")
+    assert rel_l2(out_p, out[perm]) < 1e-6
+    cperm = [3, 1, 7, 0, 2, 6, 5, 4]
+    out_c, _ = m(x[:, cperm].contiguous(), "perm")
+    assert rel_l2(out_c, out) < ACT_TOL
+    (out.square().mean() + extra).backward()
+    for k, p in m.named_parameters():
+        if k == "proxies":
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
