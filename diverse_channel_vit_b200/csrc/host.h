@@ -50,6 +50,10 @@ struct ProfScope {
   cudaStream_t st;
 };
 
+// 3-D fp32 tensor (used for the TMA reduce-add of the attention dQ accumulator)
+int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                     uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+
 #define DCV_CUDA(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
