@@ -44,7 +44,9 @@ struct AttnBwdParams {
 };
 
 // smem: K,V | Q,dO x2 stages | dS^T (2 chunks of [128 kv][64 q]) | dQ staging (2 boxes of [128 q][32] fp32)
-constexpr int kBwdSmem = 2 * kTile16K + 4 * kTile16K + 2 * kTile16K + 2 * kTile16K + 1024 + 256;
+//       | lse2 / delta of the query tile x2 stages (TMA bulk copies riding on the Q/dO barrier)
+constexpr int kStatBytes = 2 * kTq * 4;  // 128 lse2 + 128 delta
+constexpr int kBwdSmem = 2 * kTile16K + 4 * kTile16K + 2 * kTile16K + 2 * kTile16K + 2 * kStatBytes + 1024 + 256;
 constexpr int kBwdThreads = 320;
 
 __device__ __forceinline__ void wg_barrier(int g) {  // named barrier 1 + g, the 128 threads of warpgroup g
@@ -69,7 +71,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint8_t* sdO = sQ + 2 * kTile16K;   // 2 stages
   uint8_t* sdS = sdO + 2 * kTile16K;  // [2 q-chunks][128 kv rows][128 B] swizzled
   uint8_t* sdQ = sdS + 2 * kTile16K;  // [2 d-halves][128 q rows][32 fp32] swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdQ + 2 * kTile16K);
+  uint8_t* sStat = sdQ + 2 * kTile16K;  // [2 stages][lse2 128 | delta 128] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * kStatBytes);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;   // [2]
   uint64_t* qdo_empty = bars + 3;  // [2]
@@ -124,9 +127,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&qdo_full[st], 2 * kTile16K);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * kTile16K + kStatBytes);
         tma_load_3d(sQ + st * kTile16K, &map_qkv, &qdo_full[st], h * kHd, i * kTq, b);
         tma_load_3d(sdO + st * kTile16K, &map_do, &qdo_full[st], h * kHd, i * kTq, b);
+        const size_t so = (static_cast<size_t>(b) * p.H + h) * p.Lp + static_cast<size_t>(i) * kTq;
+        bulk_load_1d(sStat + st * kStatBytes, p.lse2 + so, kTq * 4, &qdo_full[st]);
+        bulk_load_1d(sStat + st * kStatBytes + kTq * 4, p.delta + so, kTq * 4, &qdo_full[st]);
       }
     }
   } else if (warp == 9) {
@@ -207,9 +213,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     const bool kv_ok = kv0 + r < p.L;
     const bool kv_tail = kv0 + kTk > p.L;     // uniform: only the last key tile has masked rows
-    const size_t stat_base = (static_cast<size_t>(b) * p.H + h) * p.Lp;
-    uint8_t* sdS_g = sdS + g * kTile16K;
-    uint8_t* sdQ_g = sdQ + g * kTile16K;
+    const uint32_t sdS_g = smem_u32(sdS + g * kTile16K);
+    const uint32_t sdQ_g = smem_u32(sdQ + g * kTile16K);
 
     auto drain_dq = [&](int i) {
       // dQ_i columns [32g, 32g+32): TMEM -> swizzled smem box -> TMA reduce-add into dq_acc
@@ -224,43 +229,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       wg_barrier(g);
 #pragma unroll
       for (int v = 0; v < 8; ++v)
-        *reinterpret_cast<uint4*>(sdQ_g + sw128_offset(r, v)) =
-            make_uint4(qreg[4 * v], qreg[4 * v + 1], qreg[4 * v + 2], qreg[4 * v + 3]);
+        st_shared_v4(sdQ_g + sw128_offset(r, v), qreg[4 * v], qreg[4 * v + 1], qreg[4 * v + 2], qreg[4 * v + 3]);
       fence_proxy_async_smem();
       wg_barrier(g);
       if (tid_g == 0) {
-        tma_reduce_add_3d(&map_dq, sdQ_g, g * 32, i * kTq, b * p.H + h);
+        tma_reduce_add_3d(&map_dq, sdQ + g * kTile16K, g * 32, i * kTq, b * p.H + h);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
 
     for (int i = 0; i < n_q; ++i) {
-      const int q0 = i * kTq + g * 64;
-      const float4* lse4 = reinterpret_cast<const float4*>(p.lse2 + stat_base + q0);
-      const float4* del4 = reinterpret_cast<const float4*>(p.delta + stat_base + q0);
-      uint32_t pk[32];  // P^T row (64 queries), packed bf16, kept for phase B
+      // lse2 / delta of this warpgroup's 64 queries (smem, broadcast reads)
+      const uint32_t s_lse = smem_u32(sStat + (i & 1) * kStatBytes) + g * 256;
+      const uint32_t s_del = s_lse + kTq * 4;
+      float pf[64];  // P^T row (64 queries) in fp32, kept for phase B
 
       // ---- phase A: P^T = exp2(S^T * sl2 - lse2[q]) ----
+      mbar_wait(&qdo_full[i & 1], (i >> 1) & 1);  // stats landed (completes long before S_i)
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sreg[32];
-        tmem_ld32(tS + lane_base + g * 64 + c * 32, sreg);
+      {
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS + lane_base + g * 64, s0);
+        tmem_ld32(tS + lane_base + g * 64 + 32, s1);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 ls = __ldg(lse4 + c * 8 + j);
-          float p0 = fast_exp2(fmaf(__uint_as_float(sreg[4 * j + 0]), p.sl2, -ls.x));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sreg[4 * j + 1]), p.sl2, -ls.y));
-          float p2 = fast_exp2(fmaf(__uint_as_float(sreg[4 * j + 2]), p.sl2, -ls.z));
-          float p3 = fast_exp2(fmaf(__uint_as_float(sreg[4 * j + 3]), p.sl2, -ls.w));
-          if (kv_tail && !kv_ok) p0 = p1 = p2 = p3 = 0.f;
-          pk[c * 16 + 2 * j] = pack_bf16(p0, p1);
-          pk[c * 16 + 2 * j + 1] = pack_bf16(p2, p3);
+          const float4 la = ld_shared_f4(s_lse + j * 16), lb = ld_shared_f4(s_lse + 128 + j * 16);
+          pf[4 * j + 0] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 0]), p.sl2, -la.x));
+          pf[4 * j + 1] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 1]), p.sl2, -la.y));
+          pf[4 * j + 2] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 2]), p.sl2, -la.z));
+          pf[4 * j + 3] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 3]), p.sl2, -la.w));
+          pf[32 + 4 * j + 0] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 0]), p.sl2, -lb.x));
+          pf[32 + 4 * j + 1] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 1]), p.sl2, -lb.y));
+          pf[32 + 4 * j + 2] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 2]), p.sl2, -lb.z));
+          pf[32 + 4 * j + 3] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 3]), p.sl2, -lb.w));
         }
-        uint32_t(&half)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]);
-        tmem_st16(tP + lane_base + g * 32 + c * 16, half);
+      }
+      if (kv_tail && !kv_ok) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) pf[j] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(pf[c * 32 + 2 * j], pf[c * 32 + 2 * j + 1]);
+        tmem_st16(tP + lane_base + g * 32 + c * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -272,28 +287,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       // ---- phase B: dS^T = P^T o (dP^T - delta[q])   (softmax scale folded into dK / dQ epilogues) ----
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t dreg[32];
-        tmem_ld32(tdP + lane_base + g * 64 + c * 32, dreg);
+      {
+        uint32_t d0[32], d1[32];
+        tmem_ld32(tdP + lane_base + g * 64, d0);
+        tmem_ld32(tdP + lane_base + g * 64 + 32, d1);
         tmem_ld_wait();
-        uint32_t dk[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 de = __ldg(del4 + c * 8 + j);
-          const float2 pa = unpack_bf16(pk[c * 16 + 2 * j]);
-          const float2 pb = unpack_bf16(pk[c * 16 + 2 * j + 1]);
-          const float d0 = pa.x * (__uint_as_float(dreg[4 * j + 0]) - de.x);
-          const float d1 = pa.y * (__uint_as_float(dreg[4 * j + 1]) - de.y);
-          const float d2 = pb.x * (__uint_as_float(dreg[4 * j + 2]) - de.z);
-          const float d3 = pb.y * (__uint_as_float(dreg[4 * j + 3]) - de.w);
-          dk[2 * j] = pack_bf16(d0, d1);
-          dk[2 * j + 1] = pack_bf16(d2, d3);
+        for (int v = 0; v < 8; ++v) {  // 8 queries -> one 16-byte slot of the swizzled dS^T tile
+          const uint32_t* dr = v < 4 ? d0 : d1;
+          const int o = (v & 3) * 8;
+          const float4 da = ld_shared_f4(s_del + v * 32), db = ld_shared_f4(s_del + v * 32 + 16);
+          const float e0 = pf[v * 8 + 0] * (__uint_as_float(dr[o + 0]) - da.x);
+          const float e1 = pf[v * 8 + 1] * (__uint_as_float(dr[o + 1]) - da.y);
+          const float e2 = pf[v * 8 + 2] * (__uint_as_float(dr[o + 2]) - da.z);
+          const float e3 = pf[v * 8 + 3] * (__uint_as_float(dr[o + 3]) - da.w);
+          const float e4 = pf[v * 8 + 4] * (__uint_as_float(dr[o + 4]) - db.x);
+          const float e5 = pf[v * 8 + 5] * (__uint_as_float(dr[o + 5]) - db.y);
+          const float e6 = pf[v * 8 + 6] * (__uint_as_float(dr[o + 6]) - db.z);
+          const float e7 = pf[v * 8 + 7] * (__uint_as_float(dr[o + 7]) - db.w);
+          st_shared_v4(sdS_g + sw128_offset(r, v), pack_bf16(e0, e1), pack_bf16(e2, e3), pack_bf16(e4, e5),
+                       pack_bf16(e6, e7));
         }
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          *reinterpret_cast<uint4*>(sdS_g + sw128_offset(r, c * 4 + v)) =
-              make_uint4(dk[4 * v], dk[4 * v + 1], dk[4 * v + 2], dk[4 * v + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
