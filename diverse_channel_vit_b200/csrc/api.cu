@@ -247,6 +247,8 @@ int dcv_head_bwd(const float* d_out, const float* x_last, int B, int L, int D, c
 
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo_bytes, sbo_bytes); }
 
+int dcv_debug_attn_timeline(long long* buf) { return debug_attn_timeline(buf); }
+
 int dcv_profile_num_tags(void) { return PT_COUNT; }
 const char* dcv_profile_tag_name(int tag) { return (tag >= 0 && tag < PT_COUNT) ? kProfNames[tag] : ""; }
 

@@ -34,6 +34,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// debug timeline: when non-null, CTA (1,0,0) records clock64() stamps: slot = role * 1024 + iter * 8 + point
+__device__ long long* g_attn_timeline = nullptr;
+#define TL(role, it, pt)                                                                      \
+  do {                                                                                        \
+    if (tl) tl[(role) * 1024 + (it) * 8 + (pt)] = clock64();                                   \
+  } while (0)
+
 struct AttnBwdParams {
   int B, L, H, D, Lp;
   float sl2;    // scale * log2(e)
@@ -91,6 +98,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int n_q = (p.L + kTq - 1) / kTq;
+  long long* tl = (g_attn_timeline && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                   (warp == 9 || warp == 0 || warp == 4))
+                      ? g_attn_timeline
+                      : nullptr;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
@@ -166,8 +177,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         const uint64_t dQ_mn = make_desc_mnmajor(smem_u32(sQ + st * kTile16K), kTile16K);
         const uint64_t dO_mn = make_desc_mnmajor(smem_u32(sdO + st * kTile16K), kTile16K);
         // dV += P^T dO_i  (A = P^T from TMEM: 16 q per K step = 8 packed columns)
+        TL(0, i, 0);
         mbar_wait(p_ready, i & 1);
         tc_fence_after();
+        TL(0, i, 1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_ts(tdV, tP + 8 * k, dO_mn + 128 * k, id_kv, (i | k) ? 1u : 0u);
         // S^T of the next query tile may overwrite tS now (phase A of tile i has consumed it)
@@ -183,8 +196,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           umma_commit(s_full);
         }
         // dK += dS^T Q_i ; dQ_i = dS K
+        TL(0, i, 2);
         mbar_wait(ds_ready, i & 1);
         tc_fence_after();
+        TL(0, i, 3);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tdK, (k < 4 ? dS_k0 : dS_k1) + 2 * (k & 3), dQ_mn + 128 * k, id_kv, (i | k) ? 1u : 0u);
@@ -192,6 +207,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           mbar_wait(dq_empty, (i - 1) & 1);
           tc_fence_after();
         }
+        TL(0, i, 4);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_ss(tdQ, dS_mn + 128 * k, dK_mn + 128 * k, id_dq, k ? 1u : 0u);
         umma_commit(dq_full);
@@ -201,6 +217,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dOn_k + 2 * k, id_s, k ? 1u : 0u);
           umma_commit(dp_full);
         }
+        TL(0, i, 5);
       }
       umma_commit(dkv_full);
     }
@@ -245,9 +262,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       float pf[64];  // P^T row (64 queries) in fp32, kept for phase B
 
       // ---- phase A: P^T = exp2(S^T * sl2 - lse2[q]) ----
+      TL(1 + g, i, 0);
       mbar_wait(&qdo_full[i & 1], (i >> 1) & 1);  // stats landed (completes long before S_i)
       mbar_wait(s_full, i & 1);
       tc_fence_after();
+      TL(1 + g, i, 1);
       {
         uint32_t s0[32], s1[32];
         tmem_ld32(tS + lane_base + g * 64, s0);
@@ -280,13 +299,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
+      TL(1 + g, i, 2);
 
       // ---- drain dQ_{i-1} while the MMA warp works on dV_i / S_{i+1} ----
       if (i > 0) drain_dq(i - 1);
 
       // ---- phase B: dS^T = P^T o (dP^T - delta[q])   (softmax scale folded into dK / dQ epilogues) ----
+      TL(1 + g, i, 3);
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
+      TL(1 + g, i, 4);
       {
         uint32_t d0[32], d1[32];
         tmem_ld32(tdP + lane_base + g * 64, d0);
@@ -312,6 +334,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
+      TL(1 + g, i, 5);
     }
     drain_dq(n_q - 1);
 
@@ -414,6 +437,11 @@ __global__ void attn_bwd_finish_kernel(const float* __restrict__ dq_acc, __nv_bf
 }
 
 }  // namespace
+
+int debug_attn_timeline(long long* buf) {
+  DCV_CUDA(cudaMemcpyToSymbol(g_attn_timeline, &buf, sizeof(buf)));
+  return 0;
+}
 
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
              void* dqkv, int B, int L, int H, float scale, cudaStream_t st) {

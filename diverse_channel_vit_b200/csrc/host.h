@@ -75,6 +75,8 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
              void* dqkv, int B, int L, int H, float scale, cudaStream_t st);
 
+int debug_attn_timeline(long long* buf);
+
 // ---- rowops.cu ----
 int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D,
            float eps, cudaStream_t st);

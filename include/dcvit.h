@@ -232,6 +232,10 @@ const char* dcv_profile_tag_name(int tag);
 int dcv_profile_start(void);
 int dcv_profile_stop(double* ms_by_tag, long long* launches_by_tag, int ntags);
 
+/* debug: clock64() timeline of one CTA of the attention-backward kernel into buf (>= 3*1024 int64, device);
+ * NULL switches it off */
+int dcv_debug_attn_timeline(long long* buf);
+
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);
 
