@@ -100,6 +100,26 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
+int make_tmap_2d(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_bytes & 15))
+    return set_error(DCV_ERR_UNSUPPORTED, "TMA operand must be 16-byte aligned (ptr %p, row stride %llu)", ptr,
+                     (unsigned long long)row_stride_bytes);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(2d %s %llux%llu box %ux%u) failed: %d", is_f32 ? "f32" : "bf16",
+                     (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer, (int)r);
+  return 0;
+}
+
 int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
   EncodeTiledFn fn = encode_fn();

@@ -10,7 +10,7 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B boxes, kStages-deep ring)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma, fp32 accumulators in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue       (tcgen05.ld -> registers -> bias/GELU/residual -> global)
+//   warps 4-11  epilogue       (tcgen05.ld -> registers -> bias/GELU/residual -> swizzled smem -> TMA store)
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include "common.cuh"
@@ -45,30 +45,61 @@ struct GemmNtParams {
   const float* addend;
 };
 
-template <int BN>
-struct NtCfg {
-  static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
-  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// Epilogue staging: the 128 x BN accumulator tile leaves through shared memory in column chunks of
+// 128 bytes per row (64 bf16 or 32 fp32 columns): each epilogue thread writes its row into a
+// SWIZZLE_128B [128][128 B] buffer and one thread issues a TMA store (full-line, asynchronous,
+// M-tail clipped by the tensor map).  Inputs of the epilogue (residual / GELU pre-activation) arrive
+// the same way through TMA loads, prefetched one chunk ahead.
+constexpr int kChunkBytes = kBM * 128;  // 16 KB
+
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool kTma = EPI != EPI_EMBED;
+  static constexpr bool kF32Out = EPI == EPI_BIAS_RESID || EPI == EPI_F32 || EPI == EPI_EMBED;
+  static constexpr bool kHasIn = EPI == EPI_BIAS_RESID || EPI == EPI_DGELU;
+  static constexpr bool kTwoOut = EPI == EPI_BIAS_GELU;
+  static constexpr int kCW = kF32Out ? 32 : 64;  // columns per chunk
+  // out[2] (+ out2[2]) (+ in[2])
+  static constexpr int kStagingBytes = kTma ? (2 + (kTwoOut ? 2 : 0) + (kHasIn ? 2 : 0)) * kChunkBytes : 0;
 };
 
+template <int BN, int EPI>
+struct NtCfg {
+  static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
+  static constexpr int kStagingBytes = EpiTraits<EPI>::kStagingBytes;
+  static constexpr int kMaxStages = (232448 - 1024 - 256 - kStagingBytes) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each taking half of a chunk's columns
+constexpr int kNtThreads = 128 + kEpiWarps * 32;
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
 template <int BN, int EPI, bool kBMn>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const GemmNtParams p) {
-  using Cfg = NtCfg<BN>;
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
+               const __grid_constant__ CUtensorMap map_in, const GemmNtParams p) {
+  using Cfg = NtCfg<BN, EPI>;
+  using ET = EpiTraits<EPI>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                              // kStages x [128][64] bf16
   uint8_t* smem_b = smem + kStages * (kBM * kBK * 2);  // kStages x [BN][64] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* stage_out = smem + kStages * Cfg::kStageBytes;           // [2] x 16 KB
+  uint8_t* stage_out2 = stage_out + 2 * kChunkBytes;                // [2] (GELU second output)
+  uint8_t* stage_in = stage_out + (ET::kTwoOut ? 4 : 2) * kChunkBytes;  // [2] (residual / pre-activation)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* in_full = bars + 2 * kStages + 4;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,6 +112,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (ET::kTma) tma_prefetch_desc(&map_out);
+    if (ET::kTwoOut) tma_prefetch_desc(&map_out2);
+    if (ET::kHasIn) tma_prefetch_desc(&map_in);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -89,7 +123,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&in_full[i], 1);
     }
     fence_barrier_init();
   }
@@ -156,8 +191,146 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (warp >= 4 && ET::kTma) {
+    // ---------------- epilogue: TMEM -> registers -> swizzled smem -> TMA store ----------------
+    constexpr int CW = ET::kCW;
+    constexpr int HW = CW / 2;  // columns per thread: warps w and w+4 share a lane quadrant and split the chunk
+    constexpr int kChunks = BN / CW;
+    const int q = warp & 3;  // TMEM lane quadrant owned by this warp
+    const int half = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const int tid_e = threadIdx.x - 128;
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int total_chunks = my_tiles * kChunks;
+    auto chunk_coords = [&](int n, int& m0, int& col0) {
+      const int tile = blockIdx.x + (n / kChunks) * gridDim.x;
+      m0 = (tile / n_tiles) * kBM;
+      col0 = (tile % n_tiles) * BN + (n % kChunks) * CW;
+    };
+    if (ET::kHasIn && tid_e == 0 && total_chunks > 0) {  // prefetch the input of chunk 0
+      int m0, col0;
+      chunk_coords(0, m0, col0);
+      mbar_arrive_expect_tx(&in_full[0], kChunkBytes);
+      tma_load_2d(stage_in, &map_in, &in_full[0], col0, m0);
+    }
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int n = 0; n < total_chunks; ++n) {
+      const int c = n % kChunks;
+      const int buf = n & 1;
+      int m0, col0;
+      chunk_coords(n, m0, col0);
+      if (c == 0) {
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+      }
+      // accumulator half-chunk -> registers
+      float v[HW];
+      {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * CW + half * HW;
+        if constexpr (HW == 32) {
+          uint32_t r0[32];
+          tmem_ld32(taddr, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
+        } else {
+          uint32_t r0[16];
+          tmem_ld16(taddr, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+        }
+      }
+      if (c == kChunks - 1) {  // the whole accumulator tile has been read out
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+      if (EPI != EPI_DGELU && p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < HW; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + half * HW + i));
+          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+        }
+      }
+      // staging buffer `buf` must have been read out by the TMA store issued two chunks ago
+      if (tid_e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      epi_barrier();
+      if (ET::kHasIn) {
+        if (tid_e == 0 && n + 1 < total_chunks) {  // prefetch the next chunk's input (its buffer was consumed at n-1)
+          int m1, c1;
+          chunk_coords(n + 1, m1, c1);
+          mbar_arrive_expect_tx(&in_full[buf ^ 1], kChunkBytes);
+          tma_load_2d(stage_in + (buf ^ 1) * kChunkBytes, &map_in, &in_full[buf ^ 1], c1, m1);
+        }
+        mbar_wait(&in_full[buf], (n >> 1) & 1);
+      }
+      // this thread's four 16-byte slots of row r in the [128][128 B] swizzled staging tile
+      const uint32_t s_out = smem_u32(stage_out + buf * kChunkBytes);
+      const int j0 = half * 4;
+      if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(s_out + sw128_offset(r, j0 + j), pack_bf16(v[8 * j], v[8 * j + 1]),
+                       pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                       pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        if (EPI == EPI_BIAS_GELU) {
+          const uint32_t s_out2 = smem_u32(stage_out2 + buf * kChunkBytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(s_out2 + sw128_offset(r, j0 + j), pack_bf16(gelu_exact(v[8 * j]), gelu_exact(v[8 * j + 1])),
+                         pack_bf16(gelu_exact(v[8 * j + 2]), gelu_exact(v[8 * j + 3])),
+                         pack_bf16(gelu_exact(v[8 * j + 4]), gelu_exact(v[8 * j + 5])),
+                         pack_bf16(gelu_exact(v[8 * j + 6]), gelu_exact(v[8 * j + 7])));
+        }
+      } else if (EPI == EPI_DGELU) {
+        const uint32_t s_in = smem_u32(stage_in + buf * kChunkBytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 hraw = ld_shared_f4(s_in + sw128_offset(r, j0 + j));
+          const float2 h0 = unpack_bf16(__float_as_uint(hraw.x)), h1 = unpack_bf16(__float_as_uint(hraw.y)),
+                       h2 = unpack_bf16(__float_as_uint(hraw.z)), h3 = unpack_bf16(__float_as_uint(hraw.w));
+          st_shared_v4(s_out + sw128_offset(r, j0 + j),
+                       pack_bf16(v[8 * j + 0] * gelu_exact_grad(h0.x), v[8 * j + 1] * gelu_exact_grad(h0.y)),
+                       pack_bf16(v[8 * j + 2] * gelu_exact_grad(h1.x), v[8 * j + 3] * gelu_exact_grad(h1.y)),
+                       pack_bf16(v[8 * j + 4] * gelu_exact_grad(h2.x), v[8 * j + 5] * gelu_exact_grad(h2.y)),
+                       pack_bf16(v[8 * j + 6] * gelu_exact_grad(h3.x), v[8 * j + 7] * gelu_exact_grad(h3.y)));
+        }
+      } else {  // fp32 outputs: EPI_BIAS_RESID / EPI_F32
+        const uint32_t s_in = smem_u32(stage_in + buf * kChunkBytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (EPI == EPI_BIAS_RESID) {
+            const float4 rs = ld_shared_f4(s_in + sw128_offset(r, j0 + j));
+            o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+          }
+          st_shared_v4(s_out + sw128_offset(r, j0 + j), __float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z),
+                       __float_as_uint(o.w));
+        }
+      }
+      fence_proxy_async_smem();
+      epi_barrier();
+      if (tid_e == 0) {
+        tma_store_2d(&map_out, stage_out + buf * kChunkBytes, col0, m0);
+        if (EPI == EPI_BIAS_GELU) tma_store_2d(&map_out2, stage_out2 + buf * kChunkBytes, col0, m0);
+        tma_store_commit();
+      }
+    }
+    if (tid_e == 0) tma_store_wait0();
+  } else if (warp >= 8) {
+    // direct-store epilogue uses warps 4-7 only; these warps just keep the tmem_empty arrival count
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_full[as], aphase);  // same cadence as the reading warps
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
   } else if (warp >= 4) {
-    // -------------------------------- epilogue --------------------------------
+    // ------------------- epilogue with direct global stores (EPI_EMBED row remap) -------------------
     const int q = warp & 3;  // TMEM lane quadrant owned by this warp
     int as = 0;
     uint32_t aphase = 0;
@@ -413,10 +586,32 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ---------------------------------------------------------------------------
 static int g_tn_lbo = 0, g_tn_sbo = 0;  // debug overrides (0 = default)
 
+struct EpiMaps {
+  CUtensorMap out, out2, in;
+};
+
 template <int BN, int EPI, bool kBMn>
 static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p, cudaStream_t st) {
-  using Cfg = NtCfg<BN>;
+  using Cfg = NtCfg<BN, EPI>;
+  using ET = EpiTraits<EPI>;
   auto kern = gemm_nt_kernel<BN, EPI, kBMn>;
+  EpiMaps em;
+  em.out = em.out2 = em.in = ma;  // placeholders for the maps an epilogue does not use
+  if (ET::kTma) {
+    const uint64_t esz = ET::kF32Out ? 4 : 2;
+    void* outp = ET::kF32Out ? static_cast<void*>(p.out_f32) : static_cast<void*>(p.out_bf16);
+    if (int e = make_tmap_2d(&em.out, outp, ET::kF32Out, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * esz, ET::kCW, kBM))
+      return e;
+    if (ET::kTwoOut)
+      if (int e = make_tmap_2d(&em.out2, p.out2_bf16, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 2, ET::kCW, kBM))
+        return e;
+    if (EPI == EPI_BIAS_RESID)
+      if (int e = make_tmap_2d(&em.in, p.resid, true, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 4, ET::kCW, kBM))
+        return e;
+    if (EPI == EPI_DGELU)
+      if (int e = make_tmap_2d(&em.in, p.aux, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 2, ET::kCW, kBM))
+        return e;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     DCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -424,7 +619,7 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
   }
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  kern<<<grid, kNtThreads, Cfg::kSmemBytes, st>>>(ma, mb, em.out, em.out2, em.in, p);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -50,6 +50,9 @@ struct ProfScope {
   cudaStream_t st;
 };
 
+// 2-D row-major tensor of bf16 (is_f32 = false) or fp32 elements, 128-byte-swizzled boxes
+int make_tmap_2d(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer);
 // 3-D fp32 tensor (used for the TMA reduce-add of the attention dQ accumulator)
 int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
