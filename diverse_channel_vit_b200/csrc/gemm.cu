@@ -452,22 +452,24 @@ struct TnCfg {
   static constexpr int kABytes = kBM * kBK * 2;  // 2 MN chunks of [64 m-rows][64] bf16
   static constexpr int kBBytes = BN * kBK * 2;   // BN/64 chunks
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kStagingBytes = 2 * kChunkBytes;  // fp32 [128][32] x 2, SWIZZLE_128B
+  static constexpr int kStages = (BN <= 128) ? 6 : 4;
   static constexpr int kTmemCols = (BN <= 128) ? 128 : 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const GemmTnParams p) {
+               const __grid_constant__ CUtensorMap map_c, const GemmTnParams p) {
   using Cfg = TnCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* stage_c = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -546,30 +548,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         umma_commit(tmem_full);
       }
     } else if (warp >= 4) {
+      // epilogue: 32-column fp32 chunks -> swizzled smem -> TMA reduce-add (split-K) or TMA store
       const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const int tid_e = threadIdx.x - 128;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
-      const int row = n0 + q * 32 + lane;
-      const bool row_ok = row < p.Nout;
-      float* crow = p.C + static_cast<size_t>(row) * p.ldc + k0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
         tmem_ld_wait();
-        if (row_ok) {
-          if (p.use_atomic) {
+        const int buf = c & 1;
+        if (tid_e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        const uint32_t s_out = smem_u32(stage_c + buf * kChunkBytes);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(crow + c * 32 + i, __uint_as_float(r[i]));
-          } else {
-            float4* dst = reinterpret_cast<float4*>(crow + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-          }
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(s_out + sw128_offset(r, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (tid_e == 0) {
+          if (p.use_atomic) tma_reduce_add_2d(&map_c, stage_c + buf * kChunkBytes, k0 + c * 32, n0);
+          else tma_store_2d(&map_c, stage_c + buf * kChunkBytes, k0 + c * 32, n0);
+          tma_store_commit();
         }
       }
+      if (tid_e == 0) tma_store_wait0();
     }
   }
 
@@ -708,7 +713,9 @@ static int launch_tn(const CUtensorMap& ma, const CUtensorMap& mb, GemmTnParams 
   p.lbo_a = g_tn_lbo ? g_tn_lbo : 64 * 128;
   p.lbo_b = g_tn_lbo ? g_tn_lbo : 64 * 128;
   p.sbo = g_tn_sbo ? g_tn_sbo : 1024;
-  kern<<<tiles * splits, 256, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  CUtensorMap mc;
+  if (int e = make_tmap_2d(&mc, p.C, true, (uint64_t)p.Kout, (uint64_t)p.Nout, (uint64_t)p.ldc * 4, 32, kBM)) return e;
+  kern<<<tiles * splits, 256, Cfg::kSmemBytes, st>>>(ma, mb, mc, p);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -80,7 +80,38 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 // Persistent grid; per-lane column accumulators, one smem reduction + D atomics per CTA.
 // ---------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(kRowWarps * 32)
+struct LnBwdRow {  // one row's operands as they come from memory
+  float4 x[NV], dr[NV];
+  uint2 dy[NV];
+  float mu, rs;
+};
+
+template <int NV>
+__device__ __forceinline__ void ln_bwd_load(LnBwdRow<NV>& t, const float* __restrict__ x,
+                                            const __nv_bfloat16* __restrict__ dy, const float* __restrict__ dres,
+                                            const float* __restrict__ mean, const float* __restrict__ rstd, int row,
+                                            int D, int nvec, int lane) {
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
+  const float4* dr = reinterpret_cast<const float4*>(dres + static_cast<size_t>(row) * D);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int idx = lane + 32 * k;
+    if (idx < nvec) {
+      t.x[k] = __ldcs(xr + idx);   // streamed once: do not keep in L1/L2 longer than needed
+      t.dy[k] = __ldcs(dyr + idx);
+      t.dr[k] = __ldcs(dr + idx);
+    } else {
+      t.x[k] = t.dr[k] = make_float4(0, 0, 0, 0);
+      t.dy[k] = make_uint2(0, 0);
+    }
+  }
+  t.mu = mean[row];
+  t.rs = rstd[row];
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kRowWarps * 32, NV <= 3 ? 2 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -96,37 +127,36 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
     acc_g[k] = acc_b[k] = acc_s[k] = make_float4(0, 0, 0, 0);
   }
   const float inv_d = 1.0f / static_cast<float>(D);
-  for (int row = blockIdx.x * kRowWarps + warp; row < M; row += gridDim.x * kRowWarps) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-    const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
-    float4* dr = reinterpret_cast<float4*>(dres + static_cast<size_t>(row) * D);
-    const float mu = mean[row], rs = rstd[row];
+  const int stride = gridDim.x * kRowWarps;
+  int row = blockIdx.x * kRowWarps + warp;
+  LnBwdRow<NV> cur, nxt;
+  if (row < M) ln_bwd_load(cur, x, dy, dres, mean, rstd, row, D, nvec, lane);
+  for (; row < M; row += stride) {
+    // software pipeline: the next row's loads are in flight while this row is reduced and stored
+    if (row + stride < M) ln_bwd_load(nxt, x, dy, dres, mean, rstd, row + stride, D, nvec, lane);
     float4 xh[NV], gy[NV], dyv[NV];
     float c1 = 0.f, c2 = 0.f;
+    const float mu = cur.mu, rs = cur.rs;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int idx = lane + 32 * k;
-      if (idx < nvec) {
-        const float4 xv = xr[idx];
-        const uint2 d2 = dyr[idx];
-        const float2 d01 = unpack_bf16(d2.x), d23 = unpack_bf16(d2.y);
-        dyv[k] = make_float4(d01.x, d01.y, d23.x, d23.y);
-        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        gy[k] = make_float4(dyv[k].x * g[k].x, dyv[k].y * g[k].y, dyv[k].z * g[k].z, dyv[k].w * g[k].w);
+      const float2 d01 = unpack_bf16(cur.dy[k].x), d23 = unpack_bf16(cur.dy[k].y);
+      dyv[k] = make_float4(d01.x, d01.y, d23.x, d23.y);
+      xh[k] = make_float4((cur.x[k].x - mu) * rs, (cur.x[k].y - mu) * rs, (cur.x[k].z - mu) * rs, (cur.x[k].w - mu) * rs);
+      gy[k] = make_float4(dyv[k].x * g[k].x, dyv[k].y * g[k].y, dyv[k].z * g[k].z, dyv[k].w * g[k].w);
+      if (lane + 32 * k < nvec) {
         c1 += (gy[k].x + gy[k].y) + (gy[k].z + gy[k].w);
         c2 += (gy[k].x * xh[k].x + gy[k].y * xh[k].y) + (gy[k].z * xh[k].z + gy[k].w * xh[k].w);
-      } else {
-        xh[k] = gy[k] = dyv[k] = make_float4(0, 0, 0, 0);
       }
     }
     c1 = warp_sum(c1) * inv_d;
     c2 = warp_sum(c2) * inv_d;
+    float4* dr = reinterpret_cast<float4*>(dres + static_cast<size_t>(row) * D);
     uint2* dxb = reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(row) * D);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int idx = lane + 32 * k;
       if (idx < nvec) {
-        float4 o = dr[idx];
+        float4 o = cur.dr[k];
         o.x += rs * (gy[k].x - c1 - xh[k].x * c2);
         o.y += rs * (gy[k].y - c1 - xh[k].y * c2);
         o.z += rs * (gy[k].z - c1 - xh[k].z * c2);
@@ -142,6 +172,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
         acc_s[k].x += o.x; acc_s[k].y += o.y; acc_s[k].z += o.z; acc_s[k].w += o.w;
       }
     }
+    cur = nxt;
   }
   // CTA reduction of the three column accumulators, one after the other through `red`
 #pragma unroll 1
@@ -257,7 +288,7 @@ int ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd,
   if (M <= 0 || D <= 0) return set_error(DCV_ERR_INVALID, "ln_bwd: empty problem");
   if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "ln_bwd: D=%d must be a multiple of 4", D);
   ProfScope prof(PT_LN_BWD, st);
-  const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 2);
+  const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 4);
   const size_t smem = static_cast<size_t>(kRowWarps) * D * sizeof(float);
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
