@@ -55,7 +55,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
   uint64_t* kv_empty = bars + 1 + kFwdStages;
   uint64_t* s_full = bars + 1 + 2 * kFwdStages;
   uint64_t* p_full = s_full + 1;
-  uint64_t* pv_full = s_full + 2;
+  uint64_t* o_full = s_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
 
   const int warp = threadIdx.x >> 5;
@@ -74,7 +74,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
     }
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
-    mbar_init(pv_full, 1);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 256);
@@ -82,7 +82,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tP = tmem_base + 128, tPV = tmem_base + 192;
+  const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -112,12 +112,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % kFwdStages;
+        // O (TMEM) += P_j V_j ; the softmax warps have rescaled O beforehand when the row max moved
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         const uint64_t dv = make_desc_mnmajor(smem_u32(sV + st * (kTk * kHd * 2)), 64 * 128);
 #pragma unroll
-        for (int k = 0; k < kTk / 16; ++k) umma_ts(tPV, tP + 8 * k, dv + 128 * k, idesc_pv, k ? 1u : 0u);
-        umma_commit(pv_full);
+        for (int k = 0; k < kTk / 16; ++k) umma_ts(tO, tP + 8 * k, dv + 128 * k, idesc_pv, (j | k) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         if (j + 1 < n_kv) {
           const int st1 = (j + 1) % kFwdStages;
@@ -126,94 +126,110 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
           const uint64_t dk = make_desc_kmajor(smem_u32(sK + st1 * (kTk * kHd * 2)));
 #pragma unroll
           for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-          umma_commit(s_full);
+          umma_commit(s_full);  // also certifies that PV_j has completed: P and O are quiescent
+        } else {
+          umma_commit(o_full);
         }
       }
     }
   } else {
     // ------------------------------ softmax warpgroup ------------------------------
+    // Thread t owns query row t: one TMEM read of the 128 scores, running max with lazy rescaling
+    // (O and l are only rescaled when the max grows by more than 2^8, so p <= 256 stays exact enough
+    // in bf16/fp32 and the TMEM round trip for O is rare), P back to TMEM as the A operand of PV.
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const int row = q0 + warp * 32 + lane;
     float m = -INFINITY, l = 0.f;
-    float o[kHd];
-#pragma unroll
-    for (int i = 0; i < kHd; ++i) o[i] = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * kTk;
       const bool tail = kv0 + kTk > p.L;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kTk / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_base + c * 32, r);
-        tmem_ld_wait();
-        if (tail) {
+      uint32_t sr[128];
+      tmem_ld32(tS + lane_base, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      tmem_ld32(tS + lane_base + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+      tmem_ld32(tS + lane_base + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
+      tmem_ld32(tS + lane_base + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+      tmem_ld_wait();
+      if (tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kv0 + c * 32 + i < p.L) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+        for (int i = 0; i < 128; ++i)
+          if (kv0 + i >= p.L) sr[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.sl2;
+      const bool grow = mx > m + 8.0f;  // first tile: m = -inf -> true
+      if (__any_sync(0xffffffffu, grow)) {
+        const float alpha = grow ? fast_exp2(m - mx) : 1.0f;  // exp2(-inf) = 0 on the first tile
+        if (grow) {
+          m = mx;
+          l *= alpha;
+        }
+        if (j > 0) {  // rescale the O accumulator in TMEM (warp-collective; lanes that did not grow use 1)
+#pragma unroll
+          for (int c = 0; c < kHd / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + lane_base + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + lane_base + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+            tmem_st16(tO + lane_base + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+          }
         }
       }
-      const float m_new = fmaxf(m, mx * p.sl2);
-      const float alpha = fast_exp2(m - m_new);
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < kTk / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_base + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.sl2, -m_new));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -m_new));
-          if (tail) {
-            if (kv0 + c * 32 + 2 * i >= p.L) p0 = 0.f;
-            if (kv0 + c * 32 + 2 * i + 1 >= p.L) p1 = 0.f;
-          }
-          sum += p0 + p1;
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c * 16 + 2 * i]), p.sl2, -m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c * 16 + 2 * i + 1]), p.sl2, -m));
+          sum0 += p0;
+          sum1 += p1;
           pk[i] = pack_bf16(p0, p1);
         }
-        tmem_st16(tP + lane_base + c * 16, pk);
+        tmem_st8(tP + lane_base + c * 8, pk);
       }
+      l += sum0 + sum1;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
-      l = l * alpha + sum;
-      m = m_new;
-
-      mbar_wait(pv_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kHd / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tPV + lane_base + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
-      }
-      tc_fence_before();
     }
 
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    // tcgen05.ld is warp-collective: every lane reads its O row, only valid rows are stored
+    uint32_t o[kHd];
+    tmem_ld32(tO + lane_base, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+    tmem_ld32(tO + lane_base + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+    tmem_ld_wait();
     if (row < p.L) {
-      const float inv = 1.0f / l;
       __nv_bfloat16* dst = p.o + (static_cast<size_t>(b) * p.L + row) * p.D + h * kHd;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
       for (int i = 0; i < kHd / 8; ++i) {
         uint4 v;
-        v.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-        v.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-        v.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-        v.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
         d4[i] = v;
       }
       p.lse2[(static_cast<size_t>(b) * p.H + h) * p.Lp + row] = m + log2f(l);
+    } else {
+      // pad rows [L, Lp): +inf makes the backward's exp2(s - lse2) vanish without a mask
+      p.lse2[(static_cast<size_t>(b) * p.H + h) * p.Lp + row] = INFINITY;
     }
   }
 
