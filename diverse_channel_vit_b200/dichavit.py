@@ -701,13 +701,14 @@ class DiChaViT(nn.Module):
 
 
 class _GradReducer:
-    """Bucketed NCCL all-reduce(avg) of the flat gradient buffer on a side stream, overlapped with the rest
-    of backward.  The flat buffer is laid out embed | block0 .. block11 | tail and backward completes it from
-    the top down, so the finished-but-unreduced region is always one contiguous range."""
+    """Bucketed all-reduce(average) of the flat gradient buffer on a side stream, overlapped with the rest of
+    backward (NCCL over NVLink on the GPUs; the same logic runs over gloo on CPU tensors in the tests).
+    The flat buffer is laid out embed | block0 .. block11 | tail and backward completes it from the top down,
+    so the finished-but-unreduced region is always one contiguous range."""
 
     BUCKET_BLOCKS = 3
 
-    def __init__(self, module: "DiChaViT", gflat: torch.Tensor):
+    def __init__(self, module, gflat: torch.Tensor):
         import torch.distributed as dist
 
         self.dist = dist
@@ -715,10 +716,15 @@ class _GradReducer:
         self.g = gflat
         self.bounds = {n: (a, b) for n, a, b in module._groups}
         self.overlap = bool(getattr(module, "_overlap", True))
-        if module._comm_stream is None:
-            module._comm_stream = torch.cuda.Stream(device=gflat.device)
-        self.stream = module._comm_stream
+        self.world = dist.get_world_size(group=module._pg)
+        self.cuda = gflat.is_cuda
+        self.stream = None
+        if self.cuda:
+            if module._comm_stream is None:
+                module._comm_stream = torch.cuda.Stream(device=gflat.device)
+            self.stream = module._comm_stream
         self.works = []
+        self.ranges = []  # (lo, hi) launched, for inspection by tests
         self.lo: Optional[int] = None
         self.hi: Optional[int] = None
         self.n = 0
@@ -726,12 +732,19 @@ class _GradReducer:
     def _launch(self, lo: int, hi: int) -> None:
         if hi <= lo:
             return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self.stream.wait_event(ev)
-        with torch.cuda.stream(self.stream):
-            self.works.append(self.dist.all_reduce(self.g[lo:hi], op=self.dist.ReduceOp.AVG, group=self.m._pg,
-                                                   async_op=True))
+        self.ranges.append((lo, hi))
+        chunk = self.g[lo:hi]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.stream.wait_event(ev)
+            with torch.cuda.stream(self.stream):
+                chunk.mul_(1.0 / self.world)  # pre-scale: SUM of pre-scaled shards == AVG, NVLS-friendly
+                self.works.append(self.dist.all_reduce(chunk, op=self.dist.ReduceOp.SUM, group=self.m._pg,
+                                                       async_op=True))
+        else:
+            chunk.mul_(1.0 / self.world)
+            self.works.append(self.dist.all_reduce(chunk, op=self.dist.ReduceOp.SUM, group=self.m._pg, async_op=True))
 
     def ready(self, name: str, flush: bool = False) -> None:
         """The gradients of parameter group `name` are complete on the current stream."""
@@ -753,7 +766,8 @@ class _GradReducer:
             self._launch(self.lo, self.hi)
         for wk in self.works:
             wk.wait()
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
 
 
 class _DiChaViTFn(torch.autograd.Function):
