@@ -302,6 +302,12 @@ def ours(args, wname):
     lib.dcv_profile_stop(msb, cnt, ntags)
     prof = {names[i]: {"ms_per_step": msb[i] / kp, "launches_per_step": cnt[i] / kp} for i in range(ntags) if cnt[i]}
     model.feature_extractor.patch_embed.enable_sample = w["sample"]
+    # same breakdown over the timed workload itself (seeded DCS draws, variable L)
+    barrier()
+    lib.dcv_profile_start()
+    timed(K, False, 2025)
+    lib.dcv_profile_stop(msb, cnt, ntags)
+    prof_dcs = {names[i]: round(msb[i] / K, 4) for i in range(ntags) if cnt[i]}
 
     D = model.dim
     L = 1 + w["channels"] * (w["img"] // w["patch"]) ** 2
@@ -358,6 +364,7 @@ def ours(args, wname):
                           "model_tflops": None},
         "roofline": roof,
         "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+        "kernel_breakdown_dcs_ms_per_step": dict(sorted(prof_dcs.items(), key=lambda kv: -kv[1])),
         "attn_tflops": attn_tf, "attn_frac_of_peak": (attn_tf / peak_tf) if attn_tf else None,
         "cpu_baseline": cpu,
     }

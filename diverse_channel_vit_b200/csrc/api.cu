@@ -267,6 +267,8 @@ int dcv_head_bwd(const float* d_out, const float* x_last, int B, int L, int D, c
 
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo_bytes, sbo_bytes); }
 
+void dcv_debug_set_nt_cluster(int cm) { debug_set_nt_cluster(cm); }
+
 int dcv_debug_attn_timeline(long long* buf) { return debug_attn_timeline(buf); }
 
 int dcv_profile_num_tags(void) { return PT_COUNT; }

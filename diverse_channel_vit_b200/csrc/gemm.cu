@@ -78,7 +78,11 @@ constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each taking h
 constexpr int kNtThreads = 128 + kEpiWarps * 32;
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
-template <int BN, int EPI, bool kBMn>
+// CM > 1: thread-block cluster of CM CTAs working on CM consecutive M-tiles of the same N-tile.  Every CTA loads
+// its own A tile and 1/CM of the shared B tile, multicasting that slice into the shared memory of all CTAs of the
+// cluster: L2 -> SM operand traffic per CTA drops from (128 + BN) to (128 + BN / CM) rows per K step (the L2
+// bandwidth, ~6.3 KB/clk chip-wide, is what caps a 128 x 192 single-CTA tile at ~1 PFLOP/s).
+template <int BN, int EPI, bool kBMn, int CM>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
@@ -106,8 +110,20 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int n_tiles = p.N / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
+  // work distribution: "cluster tiles" of CM consecutive M-tiles x one N-tile, M-major so that CTAs running at the
+  // same time share A panels in L2; every CTA of a cluster runs the same number of iterations
+  const int crank = CM > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CM;
+  const int num_clusters = gridDim.x / CM;
+  const int num_ct = ((m_tiles + CM - 1) / CM) * n_tiles;
+  const int my_iters = cluster_id < num_ct ? (num_ct - cluster_id + num_clusters - 1) / num_clusters : 0;
+  auto tile_coords = [&](int it, int& m0, int& n0) {
+    const int ct = cluster_id + it * num_clusters;
+    m0 = ((ct / n_tiles) * CM + crank) * kBM;  // may lie beyond M (odd tail): TMA zero-fills loads, clips stores
+    n0 = (ct % n_tiles) * BN;
+  };
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CM) - 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -119,7 +135,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CM);  // released by the MMA warp of every CTA that received the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -130,7 +146,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if (CM > 1) cluster_sync_all();  // peers' barriers must be initialised before remote arrives / multicast writes
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -139,22 +156,31 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM;
-        const int n0 = (tile % n_tiles) * BN;
+      for (int it = 0; it < my_iters; ++it) {
+        int m0, n0;
+        tile_coords(it, m0, n0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          // bytes landing in THIS CTA's stage: own A tile + all CM slices of B
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(smem_a + stage * (kBM * kBK * 2), &map_a, &full_bar[stage], kb * kBK, m0);
+          uint8_t* sb = smem_b + stage * (BN * kBK * 2);
           if (kBMn) {
             // B stored [K rows][N cols] (e.g. a weight W[out,in] used as dY*W): MN-major boxes of
-            // [64 reduction rows][64 output columns]
+            // [64 reduction rows][64 output columns]; a cluster slice is 64/CM reduction rows of every box
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(smem_b + stage * (BN * kBK * 2) + c * (64 * 128), &map_b, &full_bar[stage], n0 + c * 64,
-                          kb * kBK);
+            for (int c = 0; c < BN / 64; ++c) {
+              if (CM > 1)
+                tma_load_2d_mc(sb + c * (64 * 128) + crank * (kBK / CM) * 128, &map_b, &full_bar[stage], n0 + c * 64,
+                               kb * kBK + crank * (kBK / CM), kMcMask);
+              else
+                tma_load_2d(sb + c * (64 * 128), &map_b, &full_bar[stage], n0 + c * 64, kb * kBK);
+            }
+          } else if (CM > 1) {
+            tma_load_2d_mc(sb + crank * (BN / CM) * 128, &map_b, &full_bar[stage], kb * kBK, n0 + crank * (BN / CM),
+                           kMcMask);
           } else {
-            tma_load_2d(smem_b + stage * (BN * kBK * 2), &map_b, &full_bar[stage], kb * kBK, n0);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -168,7 +194,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < my_iters; ++it) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -184,7 +210,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // MN-major: 16 reduction rows = 2048 bytes
             umma_ss(d_tmem, da + 2 * k, db + (kBMn ? 128 : 2) * k, idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CM > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);
@@ -200,12 +227,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = (warp - 4) >> 2;
     const int r = q * 32 + lane;
     const int tid_e = threadIdx.x - 128;
-    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int total_chunks = my_tiles * kChunks;
+    const int total_chunks = my_iters * kChunks;
     auto chunk_coords = [&](int n, int& m0, int& col0) {
-      const int tile = blockIdx.x + (n / kChunks) * gridDim.x;
-      m0 = (tile / n_tiles) * kBM;
-      col0 = (tile % n_tiles) * BN + (n % kChunks) * CW;
+      int n0;
+      tile_coords(n / kChunks, m0, n0);
+      col0 = n0 + (n % kChunks) * CW;
     };
     if (ET::kHasIn && tid_e == 0 && total_chunks > 0) {  // prefetch the input of chunk 0
       int m0, col0;
@@ -324,7 +350,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // direct-store epilogue uses warps 4-7 only; these warps just keep the tmem_empty arrival count
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = 0; it < my_iters; ++it) {
       mbar_wait(&tmem_full[as], aphase);  // same cadence as the reading warps
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
@@ -334,9 +360,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quadrant owned by this warp
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * kBM;
-      const int n0 = (tile % n_tiles) * BN;
+    for (int it = 0; it < my_iters; ++it) {
+      int m0, n0;
+      tile_coords(it, m0, n0);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -427,7 +453,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CM > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -595,11 +622,11 @@ struct EpiMaps {
   CUtensorMap out, out2, in;
 };
 
-template <int BN, int EPI, bool kBMn>
+template <int BN, int EPI, bool kBMn, int CM>
 static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p, cudaStream_t st) {
   using Cfg = NtCfg<BN, EPI>;
   using ET = EpiTraits<EPI>;
-  auto kern = gemm_nt_kernel<BN, EPI, kBMn>;
+  auto kern = gemm_nt_kernel<BN, EPI, kBMn, CM>;
   EpiMaps em;
   em.out = em.out2 = em.in = ma;  // placeholders for the maps an epilogue does not use
   if (ET::kTma) {
@@ -622,35 +649,55 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
     DCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kNtThreads, Cfg::kSmemBytes, st>>>(ma, mb, em.out, em.out2, em.in, p);
-  DCV_CUDA(cudaGetLastError());
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int num_ct = ((m_tiles + CM - 1) / CM) * (p.N / BN);
+  const int max_clusters = num_sms() / CM;
+  const int clusters = num_ct < max_clusters ? num_ct : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CM);
+  cfg.blockDim = dim3(kNtThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CM;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CM > 1 ? 1 : 0;
+  DCV_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, em.out, em.out2, em.in, p));
   count_launch();
   return 0;
 }
 
-template <int BN>
+template <int BN, int CM>
 static int dispatch_nt_epi(int epi, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p,
                            cudaStream_t st) {
   if (b_mn) {  // dgrad flavours only
     switch (epi) {
-      case EPI_BIAS: return launch_nt<BN, EPI_BIAS, true>(ma, mb, p, st);
-      case EPI_DGELU: return launch_nt<BN, EPI_DGELU, true>(ma, mb, p, st);
-      case EPI_F32: return launch_nt<BN, EPI_F32, true>(ma, mb, p, st);
+      case EPI_BIAS: return launch_nt<BN, EPI_BIAS, true, CM>(ma, mb, p, st);
+      case EPI_DGELU: return launch_nt<BN, EPI_DGELU, true, CM>(ma, mb, p, st);
+      case EPI_F32: return launch_nt<BN, EPI_F32, true, CM>(ma, mb, p, st);
     }
     return set_error(DCV_ERR_UNSUPPORTED, "gemm_nn: epilogue %d not instantiated", epi);
   }
   switch (epi) {
-    case EPI_BIAS: return launch_nt<BN, EPI_BIAS, false>(ma, mb, p, st);
-    case EPI_BIAS_GELU: return launch_nt<BN, EPI_BIAS_GELU, false>(ma, mb, p, st);
-    case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID, false>(ma, mb, p, st);
-    case EPI_DGELU: return launch_nt<BN, EPI_DGELU, false>(ma, mb, p, st);
-    case EPI_F32: return launch_nt<BN, EPI_F32, false>(ma, mb, p, st);
-    case EPI_EMBED: return launch_nt<BN, EPI_EMBED, false>(ma, mb, p, st);
+    case EPI_BIAS: return launch_nt<BN, EPI_BIAS, false, CM>(ma, mb, p, st);
+    case EPI_BIAS_GELU: return launch_nt<BN, EPI_BIAS_GELU, false, CM>(ma, mb, p, st);
+    case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID, false, CM>(ma, mb, p, st);
+    case EPI_DGELU: return launch_nt<BN, EPI_DGELU, false, CM>(ma, mb, p, st);
+    case EPI_F32: return launch_nt<BN, EPI_F32, false, CM>(ma, mb, p, st);
+    case EPI_EMBED:
+      if (CM == 1) return launch_nt<BN, EPI_EMBED, false, 1>(ma, mb, p, st);
+      break;
   }
   return set_error(DCV_ERR_INVALID, "gemm_nt: unknown epilogue %d", epi);
 }
+
+// Cluster size along M for the multicast B operand.  Measured on B200 at the ViT-S shapes (K or N = 384): no gain
+// (qkv 50.2 us without vs 51.8 us with a 2-CTA cluster) -- these GEMMs sit at the HBM ridge, not at the L2 -> SM
+// limit -- so the default stays 1; dcv_debug_set_nt_cluster(2) switches the multicast path on.
+static int g_nt_cluster = 1;
 
 // b_mn = false: B is [N][K] (K contiguous);  b_mn = true: B is [K][N] (N contiguous)
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
@@ -665,12 +712,14 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   else if (N % 64 == 0) bn = 64;
   else return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: N=%d must be a multiple of 64", N);
   ProfScope prof(b_mn ? PT_GEMM_NN : (epi == EPI_EMBED ? PT_EMBED_GEMM : PT_GEMM_NT), st);
+  const int cm = (epi == EPI_EMBED || M <= kBM) ? 1 : g_nt_cluster;
   CUtensorMap ma, mb;
   if (int e = make_tmap_bf16_2d(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM)) return e;
+  // B boxes are 1/cm of the tile: each CTA of a cluster fetches one slice and multicasts it
   if (b_mn) {
-    if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, kBK)) return e;
+    if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, kBK / cm)) return e;
   } else {
-    if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, bn)) return e;
+    if (int e = make_tmap_bf16_2d(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, bn / cm)) return e;
   }
   GemmNtParams p;
   p.M = M; p.N = N; p.K = K; p.ldo = ldo; p.bias = bias;
@@ -684,12 +733,21 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
     return set_error(DCV_ERR_INVALID, "gemm_nt: EPI_EMBED needs addend, T>0, L>T, M %% T == 0");
   if ((epi == EPI_BIAS_GELU && !out2) || (epi == EPI_BIAS_RESID && !resid) || (epi == EPI_DGELU && !aux) || !out)
     return set_error(DCV_ERR_INVALID, "gemm_nt: missing buffer for epilogue %d", epi);
+  if (cm == 2) {
+    switch (bn) {
+      case 192: return dispatch_nt_epi<192, 2>(epi, b_mn, ma, mb, p, st);
+      case 128: return dispatch_nt_epi<128, 2>(epi, b_mn, ma, mb, p, st);
+      default: return dispatch_nt_epi<64, 2>(epi, b_mn, ma, mb, p, st);
+    }
+  }
   switch (bn) {
-    case 192: return dispatch_nt_epi<192>(epi, b_mn, ma, mb, p, st);
-    case 128: return dispatch_nt_epi<128>(epi, b_mn, ma, mb, p, st);
-    default: return dispatch_nt_epi<64>(epi, b_mn, ma, mb, p, st);
+    case 192: return dispatch_nt_epi<192, 1>(epi, b_mn, ma, mb, p, st);
+    case 128: return dispatch_nt_epi<128, 1>(epi, b_mn, ma, mb, p, st);
+    default: return dispatch_nt_epi<64, 1>(epi, b_mn, ma, mb, p, st);
   }
 }
+
+void debug_set_nt_cluster(int cm) { g_nt_cluster = (cm == 2) ? 2 : 1; }
 
 template <int BN>
 static int launch_tn(const CUtensorMap& ma, const CUtensorMap& mb, GemmTnParams p, cudaStream_t st) {

@@ -72,6 +72,7 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
 int gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
             int accumulate, int splits, cudaStream_t st);
 void debug_set_tn_desc(int lbo, int sbo);
+void debug_set_nt_cluster(int cm);
 
 // ---- attention.cu ----
 int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st);

@@ -232,6 +232,9 @@ const char* dcv_profile_tag_name(int tag);
 int dcv_profile_start(void);
 int dcv_profile_stop(double* ms_by_tag, long long* launches_by_tag, int ntags);
 
+/* debug: cluster size (1 or 2) of the B-operand TMA multicast in dcv_gemm_nt / dcv_gemm_nn (default 1) */
+void dcv_debug_set_nt_cluster(int cm);
+
 /* debug: clock64() timeline of one CTA of the attention-backward kernel into buf (>= 3*1024 int64, device);
  * NULL switches it off */
 int dcv_debug_attn_timeline(long long* buf);
