@@ -238,6 +238,19 @@ int dcv_block_bwd(const dcv_dims* dims, const dcv_block_params* p, const dcv_blo
   return block_bwd(*dims, *p, *a, *g, *ws, dres, dres_bf16, dbias_prev, ST(stream));
 }
 
+int dcv_block_fwd_cls(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a, void* stream) {
+  if (!dims || !p || !a) return set_error(DCV_ERR_INVALID, "dcv_block_fwd_cls: null struct");
+  return block_fwd_cls(*dims, *p, *a, ST(stream));
+}
+
+int dcv_block_bwd_cls(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a,
+                      const dcv_block_grads* g, const dcv_block_ws* ws, float* dres_c, void* dres_c_bf16,
+                      float* dres, void* dres_bf16, float* dbias_prev, void* stream) {
+  if (!dims || !p || !a || !g || !ws || !dres_c || !dres_c_bf16 || !dres || !dres_bf16)
+    return set_error(DCV_ERR_INVALID, "dcv_block_bwd_cls: null struct / pointer");
+  return block_bwd_cls(*dims, *p, *a, *g, *ws, dres_c, dres_c_bf16, dres, dres_bf16, dbias_prev, ST(stream));
+}
+
 int dcv_embed_fwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const float* x,
                   const int* idx, const int* gid, const dcv_embed_acts* a, void* stream) {
   if (!dims || !cfg || !p || !a) return set_error(DCV_ERR_INVALID, "dcv_embed_fwd: null struct");

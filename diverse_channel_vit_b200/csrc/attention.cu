@@ -241,7 +241,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
   }
 }
 
-int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st) {
+int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st, int q_tiles) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(DCV_ERR_INVALID, "attn_fwd: empty problem");
   const int D = H * kHd;
   CUtensorMap map;
@@ -259,7 +259,8 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
   p.sl2 = scale * 1.4426950408889634f;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse2 = lse2;
-  dim3 grid((L + kTq - 1) / kTq, H, B);
+  const int all_tiles = (L + kTq - 1) / kTq;
+  dim3 grid(q_tiles > 0 && q_tiles < all_tiles ? q_tiles : all_tiles, H, B);
   ProfScope prof(PT_ATTN_FWD, st);
   attn_fwd_kernel<<<grid, 192, kFwdSmem, st>>>(map, p);
   DCV_CUDA(cudaGetLastError());

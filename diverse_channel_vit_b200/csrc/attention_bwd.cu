@@ -43,6 +43,7 @@ __device__ long long* g_attn_timeline = nullptr;
 
 struct AttnBwdParams {
   int B, L, H, D, Lp;
+  int n_q;      // query tiles to visit (all, or 1 when only the CLS rows carry gradient)
   float sl2;    // scale * log2(e)
   float scale;
   const float* lse2;   // [B,H,Lp]
@@ -97,7 +98,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   const int kv0 = blockIdx.x * kTk;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const int n_q = (p.L + kTq - 1) / kTq;
+  const int n_q = p.n_q;
   long long* tl = (g_attn_timeline && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
                    (warp == 9 || warp == 0 || warp == 4))
                       ? g_attn_timeline
@@ -413,6 +414,21 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const 
   }
 }
 
+// CLS-only variant: dO compact [B, D]; delta[b,h,0] = dO[b] . o[b, row 0]; delta[b,h,1..127] = 0
+__global__ void attn_bwd_prep_cls_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
+                                         float* __restrict__ delta, int B, int L, int H, int Lp) {
+  const int bh = blockIdx.x;  // one warp-sized CTA per (image, head)
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * kHd;
+  const int lane = threadIdx.x;
+  const __nv_bfloat162 a = reinterpret_cast<const __nv_bfloat162*>(o + static_cast<size_t>(b) * L * D + h * kHd)[lane];
+  const __nv_bfloat162 g = reinterpret_cast<const __nv_bfloat162*>(dO + static_cast<size_t>(b) * D + h * kHd)[lane];
+  const float2 x = __bfloat1622float2(a), y = __bfloat1622float2(g);
+  const float acc = warp_sum(x.x * y.x + x.y * y.y);
+  float* dst = delta + static_cast<size_t>(bh) * Lp;
+  for (int i = lane; i < 128; i += 32) dst[i] = (i == 0) ? acc : 0.f;
+}
+
 // scale * dq_acc fp32 [B,H,L,64] -> dqkv bf16 [B,L,3D] columns [h*64, h*64+64)
 __global__ void attn_bwd_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, int B,
                                        int L, int H, float scale) {
@@ -444,7 +460,7 @@ int debug_attn_timeline(long long* buf) {
 }
 
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
-             void* dqkv, int B, int L, int H, float scale, cudaStream_t st) {
+             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(DCV_ERR_INVALID, "attn_bwd: empty problem");
   const int D = H * kHd;
   const int Lp = (L + 127) / 128 * 128;
@@ -452,8 +468,10 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   if (int e = make_tmap_bf16_3d(&map_qkv, qkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D * 2,
                                 (uint64_t)L * 3 * D * 2, kHd, kTq, 1))
     return e;
-  if (int e = make_tmap_bf16_3d(&map_do, dO, (uint64_t)D, (uint64_t)L, (uint64_t)B, (uint64_t)D * 2,
-                                (uint64_t)L * D * 2, kHd, kTq, 1))
+  // cls_only: one gradient row per image; rows 1..127 of the query tile come back as TMA zero fill
+  const uint64_t do_rows = cls_only ? 1 : (uint64_t)L;
+  if (int e = make_tmap_bf16_3d(&map_do, dO, (uint64_t)D, do_rows, (uint64_t)B, (uint64_t)D * 2,
+                                do_rows * D * 2, kHd, kTq, 1))
     return e;
   if (int e = make_tmap_f32_3d(&map_dq, dq_acc, 64, (uint64_t)L, (uint64_t)B * H, 64 * 4, (uint64_t)L * 64 * 4, 32, kTq, 1))
     return e;
@@ -464,14 +482,20 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   }
   {
     ProfScope prof(PT_ATTN_BWD_PREP, st);
-    const long long total = static_cast<long long>(B) * L * H * 8;
-    attn_bwd_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(dO), delta, B, L, H, Lp);
+    if (cls_only) {
+      attn_bwd_prep_cls_kernel<<<B * H, 32, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(o),
+                                                     reinterpret_cast<const __nv_bfloat16*>(dO), delta, B, L, H, Lp);
+    } else {
+      const long long total = static_cast<long long>(B) * L * H * 8;
+      attn_bwd_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(dO), delta, B, L, H, Lp);
+    }
     DCV_CUDA(cudaGetLastError());
     DCV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * H * L * kHd * sizeof(float), st));
   }
   AttnBwdParams p;
   p.B = B; p.L = L; p.H = H; p.D = D; p.Lp = Lp;
+  p.n_q = cls_only ? 1 : (L + kTq - 1) / kTq;
   p.scale = scale;
   p.sl2 = scale * 1.4426950408889634f;
   p.lse2 = lse2; p.delta = delta;

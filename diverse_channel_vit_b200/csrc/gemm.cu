@@ -32,7 +32,8 @@ enum GemmEpilogue : int {
 
 struct GemmNtParams {
   int M, N, K;
-  int ldo;  // leading dimension (elements) of out / out2 / resid / aux
+  int ldo;   // leading dimension (elements) of out / out2
+  int ldin;  // leading dimension of the epilogue input (resid / aux); == ldo unless rows are gathered
   const float* bias;
   __nv_bfloat16* out_bf16;
   __nv_bfloat16* out2_bf16;
@@ -638,10 +639,10 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
       if (int e = make_tmap_2d(&em.out2, p.out2_bf16, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 2, ET::kCW, kBM))
         return e;
     if (EPI == EPI_BIAS_RESID)
-      if (int e = make_tmap_2d(&em.in, p.resid, true, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 4, ET::kCW, kBM))
+      if (int e = make_tmap_2d(&em.in, p.resid, true, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 4, ET::kCW, kBM))
         return e;
     if (EPI == EPI_DGELU)
-      if (int e = make_tmap_2d(&em.in, p.aux, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 2, ET::kCW, kBM))
+      if (int e = make_tmap_2d(&em.in, p.aux, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 2, ET::kCW, kBM))
         return e;
   }
   static bool attr_done = false;
@@ -702,7 +703,7 @@ static int g_nt_cluster = 1;
 // b_mn = false: B is [N][K] (K contiguous);  b_mn = true: B is [K][N] (N contiguous)
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
             void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st,
-            int map_T, int map_L, const float* addend) {
+            int map_T, int map_L, const float* addend, int ldin) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(DCV_ERR_INVALID, "gemm_nt: empty problem %dx%dx%d", M, N, K);
   if (K % 8 || lda % 8 || ldb % 8 || ldo % 8)
     return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: K/lda/ldb/ldo must be multiples of 8 (16-byte rows)");
@@ -723,6 +724,8 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   }
   GemmNtParams p;
   p.M = M; p.N = N; p.K = K; p.ldo = ldo; p.bias = bias;
+  p.ldin = ldin > 0 ? ldin : ldo;
+  if (p.ldin % 8) return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: ldin must be a multiple of 8");
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out);
   p.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(out2);
   p.out_f32 = reinterpret_cast<float*>(out);

@@ -68,16 +68,20 @@ int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
 // ---- gemm.cu ----
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
             void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st,
-            int map_T = 0, int map_L = 0, const float* addend = nullptr);
+            int map_T = 0, int map_L = 0, const float* addend = nullptr, int ldin = 0);
 int gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
             int accumulate, int splits, cudaStream_t st);
 void debug_set_tn_desc(int lbo, int sbo);
 void debug_set_nt_cluster(int cm);
 
 // ---- attention.cu ----
-int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st);
+// q_tiles > 0: only the first q_tiles 128-query tiles are computed (last block: only the CLS query is consumed)
+int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float scale, cudaStream_t st,
+             int q_tiles = 0);
+// cls_only: dO is compact [B, D] (gradient of the CLS rows of o, every other row being zero); only query tile 0 is
+// visited, dK / dV / dQ are still produced for all rows
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
-             void* dqkv, int B, int L, int H, float scale, cudaStream_t st);
+             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only = false);
 
 int debug_attn_timeline(long long* buf);
 
@@ -121,6 +125,10 @@ int cls_ln_bwd(const float* dfeat, const float* x, long long row_stride, const f
 int block_fwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, cudaStream_t st);
 int block_bwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, const dcv_block_grads& g,
               const dcv_block_ws& ws, float* dres, void* dres_bf16, float* dbias_prev, cudaStream_t st);
+int block_fwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, cudaStream_t st);
+int block_bwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, const dcv_block_grads& g,
+                  const dcv_block_ws& ws, float* dres_c, void* dres_c_bf16, float* dres, void* dres_bf16,
+                  float* dbias_prev, cudaStream_t st);
 int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const float* x,
               const int* idx, const int* gid, const dcv_embed_acts& a, cudaStream_t st);
 int embed_bwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const int* gid,

@@ -62,6 +62,50 @@ int block_bwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts
   return 0;
 }
 
+// Last block: only the CLS row of the output is consumed (reference dichavit.py:651-652).  Everything after the
+// attention runs on B gathered rows (row stride L*D in the full-size tensors), attention on the first query tile.
+int block_fwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, cudaStream_t st) {
+  DCV_TRY(check_dims(d));
+  const int M = d.B * d.L, D = d.D, F = d.F, B = d.B, LD = d.L * d.D;
+  DCV_TRY(ln_fwd(a.x_in, p.ln1_w, p.ln1_b, a.u, a.mean1, a.rstd1, M, D, 1e-6f, st));
+  DCV_TRY(gemm_nt(a.u, D, p.qkv_w, D, M, 3 * D, D, EPI_BIAS, p.qkv_b, a.qkv, nullptr, nullptr, nullptr, 3 * D, false, st));
+  DCV_TRY(attn_fwd(a.qkv, a.o, a.lse2, d.B, d.L, d.H, 0.125f, st, 1));
+  // x_mid[b] = x_in[b, 0] + o[b, 0] Wproj^T + b : A and the residual are gathered with row stride L*D
+  DCV_TRY(gemm_nt(a.o, LD, p.proj_w, D, B, D, D, EPI_BIAS_RESID, p.proj_b, a.x_mid, nullptr, a.x_in, nullptr, D, false, st,
+                  0, 0, nullptr, LD));
+  DCV_TRY(ln_fwd(a.x_mid, p.ln2_w, p.ln2_b, a.v, a.mean2, a.rstd2, B, D, 1e-6f, st));
+  DCV_TRY(gemm_nt(a.v, D, p.fc1_w, D, B, F, D, EPI_BIAS_GELU, p.fc1_b, a.h, a.g, nullptr, nullptr, F, false, st));
+  DCV_TRY(gemm_nt(a.g, F, p.fc2_w, F, B, D, F, EPI_BIAS_RESID, p.fc2_b, a.x_out, nullptr, a.x_mid, nullptr, D, false, st));
+  return 0;
+}
+
+int block_bwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, const dcv_block_grads& g,
+                  const dcv_block_ws& ws, float* dres_c, void* dres_c_bf16, float* dres, void* dres_bf16,
+                  float* dbias_prev, cudaStream_t st) {
+  DCV_TRY(check_dims(d));
+  const int M = d.B * d.L, D = d.D, F = d.F, B = d.B, LD = d.L * d.D;
+  // ---- MLP branch on the CLS rows ----
+  DCV_TRY(gemm_nt(dres_c_bf16, D, p.fc2_w, F, B, F, D, EPI_DGELU, nullptr, ws.dh, nullptr, nullptr, a.h, F, true, st));
+  DCV_TRY(gemm_tn(dres_c_bf16, D, a.g, F, B, D, F, g.fc2_w, F, 1, 0, st));
+  DCV_TRY(gemm_nt(ws.dh, F, p.fc1_w, D, B, D, F, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
+  DCV_TRY(gemm_tn(ws.dh, F, a.v, D, B, F, D, g.fc1_w, D, 1, 0, st));
+  DCV_TRY(colsum_bf16(ws.dh, g.fc1_b, B, F, F, st));
+  DCV_TRY(ln_bwd(ws.dv, a.x_mid, a.mean2, a.rstd2, p.ln2_w, dres_c, dres_c_bf16, g.ln2_w, g.ln2_b, g.proj_b, B, D, st));
+  // ---- attention branch: only the CLS rows of the projection input carry gradient ----
+  DCV_TRY(gemm_nt(dres_c_bf16, D, p.proj_w, D, B, D, D, EPI_BIAS, nullptr, ws.d_o, nullptr, nullptr, nullptr, D, true, st));
+  DCV_TRY(gemm_tn(dres_c_bf16, D, a.o, LD, B, D, D, g.proj_w, D, 1, 0, st));
+  DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st, true));
+  DCV_TRY(gemm_nt(ws.dqkv, 3 * D, p.qkv_w, D, M, D, 3 * D, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
+  DCV_TRY(gemm_tn(ws.dqkv, 3 * D, a.u, D, M, 3 * D, D, g.qkv_w, D, 1, 0, st));
+  DCV_TRY(colsum_bf16(ws.dqkv, g.qkv_b, M, 3 * D, 3 * D, st));
+  // gradient w.r.t. the block input through the residual path: zero except the CLS rows
+  DCV_CUDA(cudaMemsetAsync(dres, 0, static_cast<size_t>(M) * D * sizeof(float), st));
+  DCV_CUDA(cudaMemcpy2DAsync(dres, static_cast<size_t>(LD) * sizeof(float), dres_c, static_cast<size_t>(D) * sizeof(float),
+                             static_cast<size_t>(D) * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+  DCV_TRY(ln_bwd(ws.dv, a.x_in, a.mean1, a.rstd1, p.ln1_w, dres, dres_bf16, g.ln1_w, g.ln1_b, dbias_prev, M, D, st));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // patch embedding
 // ---------------------------------------------------------------------------------------------

@@ -517,20 +517,22 @@ class DiChaViT(nn.Module):
         nsets = depth if keep else 1
         nx = depth + 1 if keep else 2
         for i in range(nx):
-            ar.add(f"x{i}", M * D * 4)
+            # the last block only produces the CLS row of every image (dcv_block_fwd_cls)
+            ar.add(f"x{i}", (B if keep and i == depth else M) * D * 4)
         for i in range(nsets):
+            rows = B if keep and i == depth - 1 else M  # compact tail of the last block
             ar.add(f"u{i}", M * D * 2)
             ar.add(f"mean1_{i}", M * 4)
             ar.add(f"rstd1_{i}", M * 4)
             ar.add(f"qkv{i}", M * 3 * D * 2)
             ar.add(f"o{i}", M * D * 2)
             ar.add(f"lse{i}", B * heads * Lp * 4)
-            ar.add(f"xmid{i}", M * D * 4)
-            ar.add(f"v{i}", M * D * 2)
-            ar.add(f"mean2_{i}", M * 4)
-            ar.add(f"rstd2_{i}", M * 4)
-            ar.add(f"h{i}", M * Fh * 2)
-            ar.add(f"g{i}", M * Fh * 2)
+            ar.add(f"xmid{i}", rows * D * 4)
+            ar.add(f"v{i}", rows * D * 2)
+            ar.add(f"mean2_{i}", rows * 4)
+            ar.add(f"rstd2_{i}", rows * 4)
+            ar.add(f"h{i}", rows * Fh * 2)
+            ar.add(f"g{i}", rows * Fh * 2)
         return dict(B=B, cs=cs, H=H, W=W, P=P, D=D, heads=heads, N=N, T=T, L=L, M=M, F=Fh, Lp=Lp, depth=depth,
                     arena=ar, keep=keep)
 
@@ -599,14 +601,17 @@ class DiChaViT(nn.Module):
         last = "x0"
         for i in range(pl["depth"]):
             bp, ba, last = self._block_structs(pl, base, i)
-            check(lib.dcv_block_fwd(byref(bd), byref(bp), byref(ba), st), "dcv_block_fwd")
+            if i == pl["depth"] - 1:  # only the CLS row of the last block's output is consumed
+                check(lib.dcv_block_fwd_cls(byref(bd), byref(bp), byref(ba), st), "dcv_block_fwd_cls")
+            else:
+                check(lib.dcv_block_fwd(byref(bd), byref(bp), byref(ba), st), "dcv_block_fwd")
         D = pl["D"]
         s = pl["arena"].slots
         feat = torch.empty((B, D), dtype=torch.float32, device=dev)
         head = self.classifer_head if isinstance(self.classifer_head, nn.Linear) else None
         ncls = head.out_features if head is not None else 0
         logits = torch.empty((B, ncls), dtype=torch.float32, device=dev) if head is not None else None
-        check(lib.dcv_head_fwd(c_void_p(base + s[last]), B, pl["L"], D, c_void_p(self._fptr(fe.norm.weight)),
+        check(lib.dcv_head_fwd(c_void_p(base + s[last]), B, 1, D, c_void_p(self._fptr(fe.norm.weight)),
                                c_void_p(self._fptr(fe.norm.bias)), c_void_p(feat.data_ptr()),
                                c_void_p(base + s["head_mean"]), c_void_p(base + s["head_rstd"]),
                                c_void_p(self._fptr(head.weight)) if head is not None else None,
@@ -646,6 +651,8 @@ class DiChaViT(nn.Module):
         ws.add("R", L * D * 4)
         ws.add("dpos_patch", pl["N"] * D * 4)
         ws.add("dfeat", B * D * 4)
+        ws.add("dres_c", B * D * 4)
+        ws.add("dres_c_b", B * D * 2)
         wbuf = ws.alloc(dev)
         wb = wbuf.data_ptr()
         w = ws.slots
@@ -655,11 +662,11 @@ class DiChaViT(nn.Module):
             d_out = torch.zeros((B, ncls if head is not None else D), dtype=torch.float32, device=dev)
         d_out = d_out.contiguous().float()
         last_blk = fe.blocks[-1]
-        check(lib.dcv_head_bwd(c_void_p(d_out.data_ptr()), c_void_p(base + s[state["last"]]), B, L, D,
+        check(lib.dcv_head_bwd(c_void_p(d_out.data_ptr()), c_void_p(base + s[state["last"]]), B, 1, D,
                                c_void_p(self._fptr(fe.norm.weight)), c_void_p(state["feat"].data_ptr()),
                                c_void_p(base + s["head_mean"]), c_void_p(base + s["head_rstd"]),
                                c_void_p(self._fptr(head.weight)) if head is not None else None, ncls,
-                               c_void_p(wb + w["dfeat"]), c_void_p(wb + w["dres"]), c_void_p(wb + w["dres_b"]),
+                               c_void_p(wb + w["dfeat"]), c_void_p(wb + w["dres_c"]), c_void_p(wb + w["dres_c_b"]),
                                c_void_p(gp(fe.norm.weight)), c_void_p(gp(fe.norm.bias)),
                                c_void_p(gp(head.weight)) if head is not None else None,
                                c_void_p(gp(head.bias)) if head is not None else None,
@@ -676,9 +683,15 @@ class DiChaViT(nn.Module):
                              gp(b.attn.proj.weight), gp(b.attn.proj.bias), gp(b.norm2.weight), gp(b.norm2.bias),
                              gp(b.mlp.fc1.weight), gp(b.mlp.fc1.bias), gp(b.mlp.fc2.weight), gp(b.mlp.fc2.bias))
             prev_bias = gp(fe.blocks[i - 1].mlp.fc2.bias) if i > 0 else None
-            check(lib.dcv_block_bwd(byref(bd), byref(bp), byref(ba), byref(bg), byref(bws), c_void_p(wb + w["dres"]),
-                                    c_void_p(wb + w["dres_b"]), c_void_p(prev_bias) if prev_bias else None, st),
-                  "dcv_block_bwd")
+            if i == pl["depth"] - 1:
+                check(lib.dcv_block_bwd_cls(byref(bd), byref(bp), byref(ba), byref(bg), byref(bws),
+                                            c_void_p(wb + w["dres_c"]), c_void_p(wb + w["dres_c_b"]),
+                                            c_void_p(wb + w["dres"]), c_void_p(wb + w["dres_b"]),
+                                            c_void_p(prev_bias) if prev_bias else None, st), "dcv_block_bwd_cls")
+            else:
+                check(lib.dcv_block_bwd(byref(bd), byref(bp), byref(ba), byref(bg), byref(bws),
+                                        c_void_p(wb + w["dres"]), c_void_p(wb + w["dres_b"]),
+                                        c_void_p(prev_bias) if prev_bias else None, st), "dcv_block_bwd")
             if reducer:
                 reducer.ready(f"block{i}")
         dims, ecfg, ep, eacts, _ = self._embed_structs(pl, base, state["scal"], state["C_in"], state["use_map"], dev)

@@ -154,6 +154,21 @@ int dcv_block_bwd(const dcv_dims* dims, const dcv_block_params* p, const dcv_blo
                   const dcv_block_grads* g, const dcv_block_ws* ws, float* dres, void* dres_bf16,
                   float* dbias_prev, void* stream);
 
+/* Last transformer block, exploiting that only the CLS row of its output is consumed (dichavit.py:651-652:
+ * `x = self.norm(x); return x[:, 0]`): LN1, the qkv projection and K/V stay full size, attention runs for
+ * the first 128-query tile only, and the output projection, LN2 and the MLP run on one row per image.  Results
+ * on the consumed rows are identical to dcv_block_fwd/bwd.  In `a`, the tensors after the attention are
+ * COMPACT: x_mid, v, mean2, rstd2, h, g, x_out hold B rows (not B*L); u, mean1, rstd1, qkv, o, lse2 are full
+ * size (o / lse2 are written for query rows 0..127 of every image only). */
+int dcv_block_fwd_cls(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a, void* stream);
+
+/* dres_c fp32 [B, D] (+ bf16 copy dres_c_bf16): gradient w.r.t. the CLS rows of the block output (all other rows
+ * are zero), clobbered.  On exit dres [M, D] / dres_bf16 [M, D] hold the gradient w.r.t. the whole block input.
+ * ws: dh and d_o need B rows only; dv [M, D], dqkv [M, 3D], delta, dq_acc as in dcv_block_bwd. */
+int dcv_block_bwd_cls(const dcv_dims* dims, const dcv_block_params* p, const dcv_block_acts* a,
+                      const dcv_block_grads* g, const dcv_block_ws* ws, float* dres_c, void* dres_c_bf16,
+                      float* dres, void* dres_bf16, float* dbias_prev, void* stream);
+
 /* ---- channel-adaptive patch embedding + DCS gather + CLS/pos + TDL + CDL ----
  * models/dichavit.py:110-417 (PatchEmbedPerChannel.forward: x[:, idx] gather :210, Conv3d proj :377,
  * TDL :378-389, CDL :399-402, extra loss :406-408, + channel_embed :409-411), :554-565 (CLS, pos),
@@ -212,6 +227,7 @@ int dcv_embed_bwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dc
 
 /* ---- final norm on the CLS row + classifier head (dichavit.py:651-652, :801, :855) ----
  * head_w NULL: out = feat (CHAMMI, Identity head); else logits = feat head_w^T + head_b. */
+/* x_last rows are L*D apart (L = 1 for the compact output of dcv_block_fwd_cls). */
 int dcv_head_fwd(const float* x_last, int B, int L, int D, const float* norm_w, const float* norm_b, float* feat,
                  float* mean, float* rstd, const float* head_w, const float* head_b, float* logits, int num_classes,
                  void* stream);
