@@ -224,6 +224,9 @@ def ours(args, wname):
     y_host = torch.randint(0, w["classes"], (B,), generator=gen).pin_memory()
     x_dev = x_host.to(dev)
     y_dev = y_host.to(dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    x_buf = [torch.empty_like(x_dev) for _ in range(2)]
+    y_buf = [torch.empty_like(y_dev) for _ in range(2)]
     # > 126 MB L2 flush buffer, written between timed steps is unnecessary here: one step streams several GB
     # of activations (far larger than L2); stated in config.l2.
 
@@ -248,13 +251,34 @@ def ours(args, wname):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(nsteps):
-            if e2e:
-                xd = x_host.to(dev, non_blocking=True)
-                yd = y_host.to(dev, non_blocking=True)
-                loss = step(xd, yd)
+        if e2e:
+            # the input pipeline a trainer would run: the H2D copy of step i+1 (pinned host -> device, on a copy
+            # stream, double-buffered) overlaps the compute of step i; every step's copy is inside the timed region
+            main = torch.cuda.current_stream()
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+            def upload(i):
+                sl = i & 1
+                copy_stream.wait_event(freed[sl])
+                with torch.cuda.stream(copy_stream):
+                    x_buf[sl].copy_(x_host, non_blocking=True)
+                    y_buf[sl].copy_(y_host, non_blocking=True)
+                    ready[sl].record(copy_stream)
+
+            for sl in range(2):
+                freed[sl].record(main)
+            upload(0)
+            for i in range(nsteps):
+                sl = i & 1
+                main.wait_event(ready[sl])
+                if i + 1 < nsteps:
+                    upload(i + 1)
+                loss = step(x_buf[sl], y_buf[sl])
+                freed[sl].record(main)
                 loss.item()  # D2H read of the step's result
-            else:
+        else:
+            for _ in range(nsteps):
                 step(x_dev, y_dev)
         e1.record()
         torch.cuda.synchronize()
@@ -265,7 +289,12 @@ def ours(args, wname):
         return ms.item()
 
     K, W = args.steps, args.warmup
-    timed(max(W, 3), False, 1)  # warm-up (allocator, kernel attributes, NCCL)
+    # warm-up: one full-channel step first (largest shape: activation / workspace arenas reach their final size,
+    # every kernel attribute is set), then W >= 3 steps of the workload itself
+    model.feature_extractor.patch_embed.enable_sample = False
+    timed(1, False, 1)
+    model.feature_extractor.patch_embed.enable_sample = w["sample"]
+    timed(max(W, 3), False, 1)
     clk = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     t0 = time.time()

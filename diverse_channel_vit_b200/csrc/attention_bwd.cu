@@ -12,10 +12,9 @@
 //            dK epilogue and the finish kernel.
 //   finish : scale * dq_acc fp32 [B,H,L,64] -> bf16 dqkv[:, :, 0:D]
 //
-// Warp roles (576 threads): warps 0-15 = four compute warpgroups (4 warps per SM sub-partition, so the
-// MUFU-bound exponentials of one warpgroup overlap the TMEM / shared-memory traffic of the others); warpgroup w
-// owns the query columns [32w, 32w+32) of every S^T / dP^T tile (TMEM lane = key row = 32*(warp%4)+lane) and the
-// dQ columns [16w, 16w+16); warp 16 = TMA producer; warp 17 = MMA issuer + TMEM owner.
+// Warp roles (320 threads): warps 0-7 = two compute warpgroups, warpgroup g owns the query columns
+// [64g, 64g+64) of every S^T / dP^T tile (TMEM lane = key row = 32*(warp%4)+lane) and the dQ columns
+// [32g, 32g+32); warp 8 = TMA producer; warp 9 = MMA issuer + TMEM owner.
 // TMEM columns: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,448) | P^T bf16 [448,512)
 #include "common.cuh"
 #include "host.h"
@@ -56,12 +55,10 @@ struct AttnBwdParams {
 //       | lse2 / delta of the query tile x2 stages (TMA bulk copies riding on the Q/dO barrier)
 constexpr int kStatBytes = 2 * kTq * 4;  // 128 lse2 + 128 delta
 constexpr int kBwdSmem = 2 * kTile16K + 4 * kTile16K + 2 * kTile16K + 2 * kTile16K + 2 * kStatBytes + 1024 + 256;
-constexpr int kWG = 4;                          // compute warpgroups; warpgroup w owns query columns [32w, 32w+32)
-constexpr int kBwdThreads = kWG * 128 + 64;     // + TMA producer warp + MMA issuer warp
-constexpr int kWarpTma = kWG * 4, kWarpMma = kWG * 4 + 1;
+constexpr int kBwdThreads = 320;
 
-__device__ __forceinline__ void pair_barrier(int pr) {  // named barrier 1 + pr: the 256 threads of warpgroups 2pr, 2pr+1
-  asm volatile("bar.sync %0, 256;" ::"r"(1 + pr) : "memory");
+__device__ __forceinline__ void wg_barrier(int g) {  // named barrier 1 + g, the 128 threads of warpgroup g
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
 }
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
@@ -103,11 +100,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   const int b = blockIdx.z;
   const int n_q = p.n_q;
   long long* tl = (g_attn_timeline && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
-                   (warp == kWarpMma || warp == 0 || warp == 4))
+                   (warp == 9 || warp == 0 || warp == 4))
                       ? g_attn_timeline
                       : nullptr;
 
-  if (warp == kWarpTma && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
     tma_prefetch_desc(&map_dq);
@@ -118,14 +115,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(p_ready, kWG * 128);
-    mbar_init(ds_ready, kWG * 128);
+    mbar_init(p_ready, 256);
+    mbar_init(ds_ready, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, kWG * 128);
+    mbar_init(dq_empty, 256);
     mbar_init(dkv_full, 1);
     fence_barrier_init();
   }
-  if (warp == kWarpMma) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,7 +130,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384, tP = tmem_base + 448;
 
-  if (warp == kWarpTma) {
+  if (warp == 8) {
     // ------------------------------------ TMA producer ------------------------------------
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 2 * kTile16K);
@@ -150,7 +147,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         bulk_load_1d(sStat + st * kStatBytes + kTq * 4, p.delta + so, kTq * 4, &qdo_full[st]);
       }
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == 9) {
     // ------------------------------------- MMA issuer -------------------------------------
     if (lane == 0) {
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
@@ -227,132 +224,137 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
   } else {
     // --------------------------------- compute warpgroups ---------------------------------
-    // 16 warps = 4 per SM sub-partition: the exp-bound phase A of one warpgroup overlaps the TMEM / smem
-    // traffic of the others.  Warpgroup w: query columns [32w, 32w+32) of S^T / dP^T, dQ columns [16w, 16w+16).
-    const int w = warp >> 2;                  // warpgroup
-    const int pr = w >> 1;                    // pair of warpgroups sharing one dQ staging box / dS^T chunk
+    const int g = warp >> 2;                  // column half
     const int q4 = warp & 3;                  // TMEM lane quadrant
     const int r = q4 * 32 + lane;             // key row (phases A/B) or query row (dQ drain)
-    const int tid_p = threadIdx.x & 255;      // index inside the warpgroup pair
+    const int tid_g = threadIdx.x & 127;
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     const bool kv_ok = kv0 + r < p.L;
     const bool kv_tail = kv0 + kTk > p.L;     // uniform: only the last key tile has masked rows
-    const uint32_t sdS_p = smem_u32(sdS + pr * kTile16K);
-    const uint32_t sdQ_p = smem_u32(sdQ + pr * kTile16K);
-    const int slot0 = (w & 1) * 4;            // this warpgroup's four 16-byte slots of a 128-byte row
+    const uint32_t sdS_g = smem_u32(sdS + g * kTile16K);
+    const uint32_t sdQ_g = smem_u32(sdQ + g * kTile16K);
 
     auto drain_dq = [&](int i) {
-      // dQ_i columns [16w, 16w+16): TMEM -> swizzled smem box (shared by the pair) -> TMA reduce-add into dq_acc
+      // dQ_i columns [32g, 32g+32): TMEM -> swizzled smem box -> TMA reduce-add into dq_acc
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-      uint32_t qreg[16];
-      tmem_ld16(tdQ + lane_base + w * 16, qreg);
+      uint32_t qreg[32];
+      tmem_ld32(tdQ + lane_base + g * 32, qreg);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_empty);
-      if (tid_p == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous reduce has read the box
-      pair_barrier(pr);
+      if (tid_g == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous reduce has read sdQ_g
+      wg_barrier(g);
 #pragma unroll
-      for (int v = 0; v < 4; ++v)
-        st_shared_v4(sdQ_p + sw128_offset(r, slot0 + v), qreg[4 * v], qreg[4 * v + 1], qreg[4 * v + 2], qreg[4 * v + 3]);
+      for (int v = 0; v < 8; ++v)
+        st_shared_v4(sdQ_g + sw128_offset(r, v), qreg[4 * v], qreg[4 * v + 1], qreg[4 * v + 2], qreg[4 * v + 3]);
       fence_proxy_async_smem();
-      pair_barrier(pr);
-      if (tid_p == 0) {
-        tma_reduce_add_3d(&map_dq, sdQ + pr * kTile16K, pr * 32, i * kTq, b * p.H + h);
+      wg_barrier(g);
+      if (tid_g == 0) {
+        tma_reduce_add_3d(&map_dq, sdQ + g * kTile16K, g * 32, i * kTq, b * p.H + h);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
 
     for (int i = 0; i < n_q; ++i) {
-      // lse2 / delta of this warpgroup's 32 queries (smem, broadcast reads)
-      const uint32_t s_lse = smem_u32(sStat + (i & 1) * kStatBytes) + w * 128;
+      // lse2 / delta of this warpgroup's 64 queries (smem, broadcast reads)
+      const uint32_t s_lse = smem_u32(sStat + (i & 1) * kStatBytes) + g * 256;
       const uint32_t s_del = s_lse + kTq * 4;
-      float pf[32];  // P^T row (32 queries) in fp32, kept for phase B
+      float pf[64];  // P^T row (64 queries) in fp32, kept for phase B
 
       // ---- phase A: P^T = exp2(S^T * sl2 - lse2[q]) ----
-      TL(1 + (w & 1), i, 0);
+      TL(1 + g, i, 0);
       mbar_wait(&qdo_full[i & 1], (i >> 1) & 1);  // stats landed (completes long before S_i)
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      TL(1 + (w & 1), i, 1);
+      TL(1 + g, i, 1);
       {
-        uint32_t s0[32];
-        tmem_ld32(tS + lane_base + w * 32, s0);
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS + lane_base + g * 64, s0);
+        tmem_ld32(tS + lane_base + g * 64 + 32, s1);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 la = ld_shared_f4(s_lse + j * 16);
+          const float4 la = ld_shared_f4(s_lse + j * 16), lb = ld_shared_f4(s_lse + 128 + j * 16);
           pf[4 * j + 0] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 0]), p.sl2, -la.x));
           pf[4 * j + 1] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 1]), p.sl2, -la.y));
           pf[4 * j + 2] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 2]), p.sl2, -la.z));
           pf[4 * j + 3] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 3]), p.sl2, -la.w));
+          pf[32 + 4 * j + 0] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 0]), p.sl2, -lb.x));
+          pf[32 + 4 * j + 1] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 1]), p.sl2, -lb.y));
+          pf[32 + 4 * j + 2] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 2]), p.sl2, -lb.z));
+          pf[32 + 4 * j + 3] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 3]), p.sl2, -lb.w));
         }
       }
       if (kv_tail && !kv_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pf[j] = 0.f;
+        for (int j = 0; j < 64; ++j) pf[j] = 0.f;
       }
-      {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]);
-        tmem_st16(tP + lane_base + w * 16, pk);
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(pf[c * 32 + 2 * j], pf[c * 32 + 2 * j + 1]);
+        tmem_st16(tP + lane_base + g * 32 + c * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
-      TL(1 + (w & 1), i, 2);
+      TL(1 + g, i, 2);
 
       // ---- drain dQ_{i-1} while the MMA warp works on dV_i / S_{i+1} ----
       if (i > 0) drain_dq(i - 1);
 
       // ---- phase B: dS^T = P^T o (dP^T - delta[q])   (softmax scale folded into dK / dQ epilogues) ----
-      TL(1 + (w & 1), i, 3);
+      TL(1 + g, i, 3);
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
-      TL(1 + (w & 1), i, 4);
+      TL(1 + g, i, 4);
       {
-        uint32_t d0[32];
-        tmem_ld32(tdP + lane_base + w * 32, d0);
+        uint32_t d0[32], d1[32];
+        tmem_ld32(tdP + lane_base + g * 64, d0);
+        tmem_ld32(tdP + lane_base + g * 64 + 32, d1);
         tmem_ld_wait();
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {  // 8 queries -> one 16-byte slot of the swizzled dS^T tile
+        for (int v = 0; v < 8; ++v) {  // 8 queries -> one 16-byte slot of the swizzled dS^T tile
+          const uint32_t* dr = v < 4 ? d0 : d1;
+          const int o = (v & 3) * 8;
           const float4 da = ld_shared_f4(s_del + v * 32), db = ld_shared_f4(s_del + v * 32 + 16);
-          const float e0 = pf[v * 8 + 0] * (__uint_as_float(d0[v * 8 + 0]) - da.x);
-          const float e1 = pf[v * 8 + 1] * (__uint_as_float(d0[v * 8 + 1]) - da.y);
-          const float e2 = pf[v * 8 + 2] * (__uint_as_float(d0[v * 8 + 2]) - da.z);
-          const float e3 = pf[v * 8 + 3] * (__uint_as_float(d0[v * 8 + 3]) - da.w);
-          const float e4 = pf[v * 8 + 4] * (__uint_as_float(d0[v * 8 + 4]) - db.x);
-          const float e5 = pf[v * 8 + 5] * (__uint_as_float(d0[v * 8 + 5]) - db.y);
-          const float e6 = pf[v * 8 + 6] * (__uint_as_float(d0[v * 8 + 6]) - db.z);
-          const float e7 = pf[v * 8 + 7] * (__uint_as_float(d0[v * 8 + 7]) - db.w);
-          st_shared_v4(sdS_p + sw128_offset(r, slot0 + v), pack_bf16(e0, e1), pack_bf16(e2, e3), pack_bf16(e4, e5),
+          const float e0 = pf[v * 8 + 0] * (__uint_as_float(dr[o + 0]) - da.x);
+          const float e1 = pf[v * 8 + 1] * (__uint_as_float(dr[o + 1]) - da.y);
+          const float e2 = pf[v * 8 + 2] * (__uint_as_float(dr[o + 2]) - da.z);
+          const float e3 = pf[v * 8 + 3] * (__uint_as_float(dr[o + 3]) - da.w);
+          const float e4 = pf[v * 8 + 4] * (__uint_as_float(dr[o + 4]) - db.x);
+          const float e5 = pf[v * 8 + 5] * (__uint_as_float(dr[o + 5]) - db.y);
+          const float e6 = pf[v * 8 + 6] * (__uint_as_float(dr[o + 6]) - db.z);
+          const float e7 = pf[v * 8 + 7] * (__uint_as_float(dr[o + 7]) - db.w);
+          st_shared_v4(sdS_g + sw128_offset(r, v), pack_bf16(e0, e1), pack_bf16(e2, e3), pack_bf16(e4, e5),
                        pack_bf16(e6, e7));
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
-      TL(1 + (w & 1), i, 5);
+      TL(1 + g, i, 5);
     }
     drain_dq(n_q - 1);
 
-    // ---- epilogue: dK (x scale) and dV rows of this key tile; warpgroup w writes d columns [16w, 16w+16) ----
+    // ---- epilogue: dK (x scale) and dV rows of this key tile; warpgroup g writes d columns [32g, 32g+32) ----
     mbar_wait(dkv_full, 0);
     tc_fence_after();
 #pragma unroll
     for (int which = 0; which < 2; ++which) {  // 0: dK -> column block D, 1: dV -> column block 2D
       const uint32_t tsrc = which == 0 ? tdK : tdV;
       const float mul = which == 0 ? p.scale : 1.0f;
-      uint32_t a[16];
-      tmem_ld16(tsrc + lane_base + w * 16, a);
+      uint32_t a[32];
+      tmem_ld32(tsrc + lane_base + g * 32, a);
       tmem_ld_wait();
       if (kv_ok) {
         __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + kv0 + r) * (3 * p.D) + (which + 1) * p.D +
-                             h * kHd + w * 16;
+                             h * kHd + g * 32;
         uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
+        for (int v = 0; v < 4; ++v) {
           uint4 o;
           o.x = pack_bf16(__uint_as_float(a[8 * v + 0]) * mul, __uint_as_float(a[8 * v + 1]) * mul);
           o.y = pack_bf16(__uint_as_float(a[8 * v + 2]) * mul, __uint_as_float(a[8 * v + 3]) * mul);
@@ -362,12 +364,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         }
       }
     }
-    if (tid_p == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reduces fully performed
+    if (tid_g == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reduces fully performed
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

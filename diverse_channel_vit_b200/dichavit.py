@@ -340,8 +340,8 @@ class _Arena:
         self.slots[name] = self.off
         self.off += _round_up(max(int(nbytes), 4), 256)
 
-    def alloc(self, device) -> torch.Tensor:
-        return torch.empty(max(self.off, 256), dtype=torch.uint8, device=device)
+    def alloc(self, device, at_least: int = 0) -> torch.Tensor:
+        return torch.empty(max(self.off, at_least, 256), dtype=torch.uint8, device=device)
 
 
 class DiChaViT(nn.Module):
@@ -379,6 +379,8 @@ class DiChaViT(nn.Module):
         self._pg = None
         self._comm_stream = None
         self.last_losses: Dict[str, torch.Tensor] = {}
+        self._arena_bytes: Dict[tuple, int] = {}   # forward arena size of the full-channel plan per input shape
+        self._ws_bytes: Dict[tuple, int] = {}      # backward workspace high-water mark per input shape
 
     # ------------------------------------------------------------------ parameters
     def _ordered_params(self):
@@ -585,10 +587,16 @@ class DiChaViT(nn.Module):
         if (H // P) * (W // P) != n_pos:
             raise ValueError(f"input {H}x{W} does not match the {n_pos}-patch positional grid")
         pl = self._plan(B, cs, H, W, keep)
+        # DCS changes the token count every step: always request the size of the full-channel plan so that the
+        # caching allocator hands back the same block instead of growing a new one per (B, C') shape
+        key = (B, C_in, H, W, keep)
+        if key not in self._arena_bytes:
+            self._arena_bytes[key] = self._plan(B, C_in, H, W, keep)["arena"].off
+        arena_min = self._arena_bytes[key]
         # fp32 master -> bf16 operand copy of every parameter (one launch)
         check(lib.dcv_cast_f32_bf16(c_void_p(self._flat.data_ptr()), c_void_p(self._bflat.data_ptr()),
                                     c_longlong(self._flat.numel()), st), "dcv_cast_f32_bf16")
-        arena = pl["arena"].alloc(dev)
+        arena = pl["arena"].alloc(dev, arena_min)
         base = arena.data_ptr()
         scal = torch.zeros(4, dtype=torch.float32, device=dev)  # tdl, cdl, extra
         # reference dichavit.py:529-530: raw pos_embed iff the token count equals the grid and w == h
@@ -653,7 +661,9 @@ class DiChaViT(nn.Module):
         ws.add("dfeat", B * D * 4)
         ws.add("dres_c", B * D * 4)
         ws.add("dres_c_b", B * D * 2)
-        wbuf = ws.alloc(dev)
+        wkey = (B, state["C_in"], pl["H"], pl["W"])
+        self._ws_bytes[wkey] = max(self._ws_bytes.get(wkey, 0), ws.off)
+        wbuf = ws.alloc(dev, self._ws_bytes[wkey])
         wb = wbuf.data_ptr()
         w = ws.slots
         head = self.classifer_head if isinstance(self.classifer_head, nn.Linear) else None

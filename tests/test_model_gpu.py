@@ -187,3 +187,33 @@ def test_full_size_properties_jumpcp():
         if k == "proxies":
             continue
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_so2sat_shape_all_channel_counts():
+    """BASELINE configs[3] shape: ViT-S/8, 18 channels, 32x32 (N = 16 patches/channel): every C' in 1..18 runs (the
+    CDL kernel crosses the 48 KB shared-memory default from C' = 14 on) and CDL / TDL match the oracle."""
+    import bench
+    from diverse_channel_vit_b200.dichavit import dichavit
+
+    w = bench.WORKLOADS["so2sat"]
+    cfg = bench.model_cfg(w)
+    torch.manual_seed(1)
+    m = dichavit(cfg, mapper={"train": list(range(18))}).cuda().train()
+    pe = m.feature_extractor.patch_embed
+    x = torch.randn(4, 18, 32, 32, device="cuda")
+    chan = pe.chunk_channels("train", x.device)
+    oc = O.OracleConfig(pretrained_model_name="small", img_size=32, patch_size=8,
+                        in_channel_names=[f"c{i}" for i in range(18)], num_classes=17, proxy_loss_lambda=w["l_cdl"],
+                        ortho_loss_v1_lambda=w["l_tdl"], gamma_s=w["gs"], gamma_d=w["gd"], reverse_pos_pairs=True)
+    oc.depth = 0  # oracle: embedding + losses only
+    weights = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    for cs in (1, 2, 13, 14, 16, 18):
+        idx = torch.randperm(18)[:cs].tolist()
+        it = torch.tensor(idx, dtype=torch.int32, device="cuda")
+        pe.select_channels = lambda *_a, **_k: (cs, it, chan[it.long()].to(torch.int32))
+        out, extra = m(x, "train")
+        (out.sum() + extra).backward()
+        oo = O.forward(x.cpu(), weights, oc, list(range(18)), training=True, has_head=True, indices=idx)
+        assert abs(m.last_losses["tdl"].item() - oo.tdl.item()) <= LOSS_TOL * abs(oo.tdl.item()) + 1e-7, cs
+        assert abs(m.last_losses["cdl"].item() - oo.cdl.item()) <= LOSS_TOL * abs(oo.cdl.item()) + 1e-7, cs
+        assert torch.isfinite(out).all()
