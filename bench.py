@@ -163,6 +163,52 @@ def cpu_reference_run(wname: str, steps: int, warmup: int, batch: int, seed: int
     return batch * len(times) / total, total, cores, f"{len(times)} steps of B={batch} (seeded DCS draws), after {warmup} warm-up"
 
 
+def gpu_eager_run(wname: str, batch: int, steps: int, autocast: bool, seed: int = 2025):
+    """The reference algorithm (oracle restatement = the reference's own ATen call sequence) run eagerly by PyTorch
+    ON THE GPU: cuBLAS / cuDNN / ATen library kernels, the "existing Blackwell kernels" bar of SURVEY 8(d) (R0: fp32
+    with TF32 off as the authors train; R1: torch.autocast(bfloat16), the reference's own use_amp path).  Full channels
+    (no sampling) so that the work per step is fixed.  Returns images/s."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import dichavit_oracle as O
+
+    w = WORKLOADS[wname]
+    dev = torch.device("cuda")
+    oc = O.OracleConfig(pretrained_model_name=w["size"], img_size=w["img"], patch_size=w["patch"],
+                        in_channel_names=[f"c{i}" for i in range(w["channels"])], num_classes=w["classes"],
+                        enable_sample=False, proxy_loss_lambda=w["l_cdl"], ortho_loss_v1_lambda=w["l_tdl"],
+                        gamma_s=w["gs"], gamma_d=w["gd"], reverse_pos_pairs=True, use_square=False)
+    weights = O.make_weights(oc, True, seed)
+    params = {k: v.to(dev).requires_grad_(True) for k, v in weights.items() if k != "adaptive_interface.0"}
+    opt = torch.optim.AdamW(list(params.values()), lr=4e-4, weight_decay=0.04, fused=True)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, w["channels"], w["img"], w["img"], generator=g).to(dev)
+    y = torch.randint(0, w["classes"], (batch,), generator=g).to(dev)
+    channels = list(range(w["channels"]))
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            o = O.forward(x, params, oc, channels, training=True, has_head=True)
+            loss = F.cross_entropy(o.out.float(), y) + o.extra_loss.float()
+        loss.backward()
+        opt.step()
+
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    del params, opt
+    torch.cuda.empty_cache()
+    return batch * steps / (e0.elapsed_time(e1) / 1000.0)
+
+
 def reference_arm(args, wname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -382,6 +428,19 @@ def ours(args, wname):
         ips, secs, cores, sample = cpu_reference_run(wname, 2, 1, bb)
         cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
+    # ---- PyTorch eager on the same GPU (library kernels), rank 0, N == 1 only ----
+    eager = None
+    if world == 1 and not args.no_eager:
+        try:
+            del model, opt
+            torch.cuda.empty_cache()
+            eager = {"what": "oracle restatement of the reference run eagerly by PyTorch on this GPU (cuBLAS/cuDNN/ATen), "
+                             "full channels, same batch; compare with full_channels.value",
+                     "fp32_images_per_s": gpu_eager_run(wname, B, 3, False),
+                     "bf16_autocast_images_per_s": gpu_eager_run(wname, B, 3, True)}
+        except Exception as ex:  # e.g. out of memory on a shared box: report, do not fail the bench
+            eager = {"error": repr(ex)[:200]}
+
     h2d = x_host.numel() * 4 + y_host.numel() * 8
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
@@ -402,6 +461,7 @@ def ours(args, wname):
         "kernel_breakdown_dcs_ms_per_step": dict(sorted(prof_dcs.items(), key=lambda kv: -kv[1])),
         "attn_tflops": attn_tf, "attn_frac_of_peak": (attn_tf / peak_tf) if attn_tf else None,
         "cpu_baseline": cpu,
+        "torch_eager_gpu": eager,
     }
     # algorithmic model FLOPs of the full-channel step: fwd = 2 T P^2 D + depth (24 L D^2 + 4 L^2 D) + 2 D cls
     T = L - 1
@@ -420,6 +480,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="jumpcp", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU comparison leg")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args, args.workload)

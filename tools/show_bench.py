@@ -7,3 +7,4 @@ r = d["roofline"]
 print("roofline", r["kernel"], round(r["achieved"], 1), r["unit"], "frac", round(r["frac"], 3), "share", round(r["share_of_step"], 3))
 print(d["kernel_breakdown_ms_per_step"]); print("dcs", d.get("kernel_breakdown_dcs_ms_per_step"))
 print("attn TF", d.get("attn_tflops"), "clocks", d["clocks"], "cpu", d.get("cpu_baseline"))
+print("eager", d.get("torch_eager_gpu"))
