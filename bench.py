@@ -402,11 +402,18 @@ def ours(args, wname):
     tensor_classes["gemm_tn"] = gemm_flops_fwd / 4.0
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback"
+    traffic = None
+    try:
+        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        if top in tj and "B" in tj[top] and tj[top].get("L") == L:
+            traffic = tj[top]["dram_bytes"] * B / tj[top]["B"]  # ncu capture at another batch size, linear in B
+    except Exception:
+        pass
     if top in tensor_classes:
         per_launch_ms = prof[top]["ms_per_step"] / prof[top]["launches_per_step"]
         ach = tensor_classes[top] / (per_launch_ms * 1e-3) / 1e12
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": per_launch_ms, "share_of_step": prof[top]["ms_per_step"] / (ms_prof / kp),
                 "note": "full-channel pass (L=%d); algorithmic FLOPs per launch averaged over the %d full launches and the "
                         "last block's CLS-only launch (one query tile); recompute not counted" % (L, depth - 1)}
