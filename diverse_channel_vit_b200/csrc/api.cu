@@ -219,6 +219,17 @@ int dcv_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   return cast_f32_bf16(src, dst, n, ST(stream));
 }
 
+int dcv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* clip, void* stream) {
+  if (!p || !g || !m || !v) return set_error(DCV_ERR_INVALID, "dcv_adamw_step: null pointer");
+  return adamw_step(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, clip, ST(stream));
+}
+
+int dcv_sumsq_f32(const float* g, long long n, float* out, void* stream) {
+  if (!g || !out) return set_error(DCV_ERR_INVALID, "dcv_sumsq_f32: null pointer");
+  return sumsq_f32(g, n, out, ST(stream));
+}
+
 int dcv_sgemm_small(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
                     const float* bias, int accumulate, int M, int N, int K, void* stream) {
   if (!A || !B || !C) return set_error(DCV_ERR_INVALID, "dcv_sgemm_small: null pointer");

@@ -93,6 +93,9 @@ int ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd,
 int colsum_bf16(const void* a, float* out, int M, int N, int lda, cudaStream_t st);
 int colsum_f32(const float* a, float* out, int M, int N, int lda, cudaStream_t st);
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st);
+int adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+               float beta2, float eps, float wd, int step, const float* clip, cudaStream_t st);
+int sumsq_f32(const float* g, long long n, float* out, cudaStream_t st);
 
 // ---- embed.cu ----
 int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, int Cs, int H, int W, int P,

@@ -3,6 +3,8 @@
 // nn.LayerNorm, eps 1e-6, biased variance), bias-gradient column sums, and the
 // fp32 -> bf16 parameter cast.  One warp owns one row; all loads/stores are 8- or
 // 16-byte vectors, coalesced across the warp.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -260,6 +262,75 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 }
 
 // ---------------------------------------------------------------------------------
+// Fused AdamW over the flat parameter / gradient buffers (reference optimizers.py:20-21 timm AdamW ==
+// torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments), one launch per step, 16 B/param
+// read + 12 B/param written (+2 for the bf16 operand copy of the next forward).  `clip`: optional device
+// scalar pair {sum of squared gradients, max_norm}: gradients are scaled by min(1, max_norm / (norm + 1e-6))
+// like torch.nn.utils.clip_grad_norm_ (trainer.py:1003-1004).
+// ---------------------------------------------------------------------------------
+struct AdamWArgs {
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+};
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ p_bf16, long long n4, AdamWArgs a, const float* __restrict__ clip) {
+  float gs = 1.0f;
+  if (clip != nullptr) {
+    const float norm = sqrtf(clip[0]);
+    gs = fminf(1.0f, clip[1] / (norm + 1e-6f));
+  }
+  const float step_size = a.lr / a.bc1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = reinterpret_cast<float*>(&pv);
+    const float* gp = reinterpret_cast<const float*>(&gv);
+    float* mp = reinterpret_cast<float*>(&mv);
+    float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = gp[k] * gs;
+      pp[k] *= 1.0f - a.lr * a.wd;
+      mp[k] = a.beta1 * mp[k] + (1.0f - a.beta1) * gr;
+      vp[k] = a.beta2 * vp[k] + (1.0f - a.beta2) * gr * gr;
+      const float denom = sqrtf(vp[k]) / a.bc2_sqrt + a.eps;
+      pp[k] -= step_size * (mp[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (p_bf16 != nullptr) {
+      uint2 o;
+      o.x = pack_bf16(pp[0], pp[1]);
+      o.y = pack_bf16(pp[2], pp[3]);
+      reinterpret_cast<uint2*>(p_bf16)[i] = o;
+    }
+  }
+}
+
+// out[0] += sum(g^2)   (global gradient norm for clipping; out zeroed by the caller)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {
+  __shared__ float red[8];
+  float t = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    t += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(out, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
 static int nv_for(int D) { return (D + 127) / 128; }
@@ -327,6 +398,34 @@ int colsum_f32(const float* a, float* out, int M, int N, int lda, cudaStream_t s
   if (M <= 0 || N <= 0) return set_error(DCV_ERR_INVALID, "colsum_f32: empty problem");
   ProfScope prof(PT_SMALL, st);
   colsum_f32_kernel<<<(N + 127) / 128, 128, 0, st>>>(a, out, M, N, lda);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+               float beta2, float eps, float wd, int step, const float* clip, cudaStream_t st) {
+  if (n <= 0 || (n & 3)) return set_error(DCV_ERR_INVALID, "adamw_step: n must be a positive multiple of 4");
+  if (step < 1) return set_error(DCV_ERR_INVALID, "adamw_step: step counts from 1");
+  ProfScope prof(PT_CAST, st);
+  AdamWArgs a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd;
+  a.bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  a.bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
+  const long long n4 = n >> 2;
+  const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, static_cast<long long>(num_sms()) * 16));
+  adamw_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n4, a, clip);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sumsq_f32(const float* g, long long n, float* out, cudaStream_t st) {
+  if (n <= 0 || (n & 3)) return set_error(DCV_ERR_INVALID, "sumsq: n must be a positive multiple of 4");
+  ProfScope prof(PT_CAST, st);
+  const long long n4 = n >> 2;
+  const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, static_cast<long long>(num_sms()) * 8));
+  sumsq_kernel<<<blocks, 256, 0, st>>>(g, n4, out);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

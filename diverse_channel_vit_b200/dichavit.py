@@ -262,6 +262,56 @@ class PatchEmbedPerChannel(nn.Module):
         return c_new, indices.to(torch.int32), gid.to(torch.int32)
 
 
+    def leave_one_out_tokens(self, chunk_name: str, training_chunks: str, new_channel_init) -> Optional[torch.Tensor]:
+        """Eval-time channel tokens for chunks with channels unseen in training (reference dichavit.py:219-374).
+        Returns None when every channel of the chunk was seen (the branch degenerates to the plain lookup), else a
+        [C_in, D] tensor where unseen channels get a token synthesised from the training channels.  The
+        dynamic_input_corr_* modes need a `bank` attribute that nothing in the reference ever sets: like the
+        reference they raise ValueError("provide a channel_map (dict)!")."""
+        mapper = self.mapper
+        training_channels = [c for ch in str(training_chunks).split("_") for c in mapper[ch]]
+        chunk = list(mapper[chunk_name])
+        if all(c in training_channels for c in chunk):
+            return None
+        mode = getattr(new_channel_init, "value", new_channel_init)
+        if not isinstance(mode, str):
+            raise TypeError("new_channel_init must be given when the chunk has channels unseen in training")
+        chs_not_seen = [c for c in training_channels if c not in chunk]
+        bank = chs_not_seen if "not_in_chunk" in mode else training_channels
+        w = self.channel_embed.weight.detach()
+        rows, cur = [], 0
+        for c in chunk:
+            if c in training_channels:
+                rows.append(w[c][None])
+                continue
+            n = len(bank)
+            if mode in ("avg_2", "avg_2_not_in_chunk"):
+                param = w[[bank[cur], bank[(cur + 1) % n]]].mean(dim=0, keepdim=True)
+            elif mode in ("avg_3", "avg_3_not_in_chunk"):
+                param = w[[bank[cur], bank[(cur + 1) % n], bank[(cur + 2) % n]]].mean(dim=0, keepdim=True)
+            elif mode == "replicate":
+                param = w[bank[cur]][None]
+            elif mode == "zero":
+                param = torch.zeros_like(w[0])[None]
+            elif mode == "random":
+                param = w[c][None]
+            elif mode == "fixed_input_corr":
+                if not hasattr(self, "channel_map"):
+                    raise ValueError("provide a channel_map (dict)!")
+                param = w[self.channel_map[c]][None]
+            elif mode == "random_input_corr":
+                param = w[int(np.random.choice(training_channels))][None]
+            elif mode.startswith("dynamic_input_corr"):
+                if not hasattr(self, "bank"):
+                    raise ValueError("provide a channel_map (dict)!")
+                raise NotImplementedError("dynamic_input_corr_* needs an image bank the reference never provides")
+            else:
+                raise ValueError(f"Invalid new_channel_init: '{mode}'")
+            cur = (cur + 1) % n
+            rows.append(param)
+        return torch.cat(rows, dim=0).contiguous().float()
+
+
 class ChannelVisionTransformer(nn.Module):
     """Parameter layout of reference models/dichavit.py:420-516."""
 
@@ -470,30 +520,21 @@ class DiChaViT(nn.Module):
             raise DcvError("DiChaViT (B200-native) needs a CUDA tensor: there is no CPU fallback")
         if x.dim() != 4:
             raise ValueError("x must be [B, C, H, W]")
-        if training_chunks is not None and new_channel_init is not None:
-            self._check_leave_one_out(chunk_name, training_chunks)
         x = x.contiguous().float()
         self._ensure_flat(x.device)
         pe = self.feature_extractor.patch_embed
         cs, idx, gid = pe.select_channels(chunk_name, x.shape[1], x.device)
+        self._ce_override = None
+        if (not self.training) and training_chunks is not None:  # reference dichavit.py:219
+            self._ce_override = pe.leave_one_out_tokens(chunk_name, training_chunks, new_channel_init)
+            if self._ce_override is not None:
+                gid = torch.arange(cs, dtype=torch.int32, device=x.device)  # rows of the synthesised token matrix
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p, _, _ in self._layout)
         params = [p for p, _, _ in self._layout]
         out, extra = _DiChaViTFn.apply(self, x, cs, idx, gid, need_grad, *params)
         if self.training:
             return out, extra
         return out
-
-    def _check_leave_one_out(self, chunk_name, training_chunks):
-        """reference dichavit.py:219-374: channel-token synthesis for channels unseen in training.  For every
-        published config the test channels are a subset of the training channels, where that branch reduces to
-        the plain lookup done here; anything else is rejected instead of silently diverging."""
-        pe = self.feature_extractor.patch_embed
-        train_ch = set()
-        for c in str(training_chunks).split("_"):
-            if c in pe.mapper:
-                train_ch.update(pe.mapper[c])
-        if train_ch and not set(pe.mapper[chunk_name]).issubset(train_ch):
-            raise NotImplementedError("leave-one-out channel synthesis (new_channel_inits) is not implemented yet")
 
     # ------------------------------------------------------------------ engine
     def _plan(self, B: int, cs: int, H: int, W: int, keep: bool):
@@ -544,12 +585,17 @@ class DiChaViT(nn.Module):
         cfg = self.cfg
         s = pl["arena"].slots
         dims = _EmbedDims(pl["B"], C_in, pl["cs"], pl["H"], pl["W"], pl["P"], pl["D"])
-        ecfg = _EmbedCfg(float(cfg.ortho_loss_v1_lambda), float(cfg.proxy_loss_lambda), float(cfg.gamma_s),
-                         float(cfg.gamma_d), float(pe.channel_scale), int(bool(cfg.reverse_pos_pairs)),
-                         int(bool(cfg.use_square)))
+        # TDL / CDL only enter the training output (dichavit.py:856-861); the reference still evaluates them in eval
+        # mode and throws the value away -- here the kernels are simply not launched
+        l_tdl = float(cfg.ortho_loss_v1_lambda) if self.training else 0.0
+        l_cdl = float(cfg.proxy_loss_lambda) if self.training else 0.0
+        ecfg = _EmbedCfg(l_tdl, l_cdl, float(cfg.gamma_s), float(cfg.gamma_d), float(pe.channel_scale),
+                         int(bool(cfg.reverse_pos_pairs)), int(bool(cfg.use_square)))
         has_prox = hasattr(pe, "channel_emb_proxies")
         pos_map = self._pos_map(pl["W"], pl["H"], device) if use_map else None
-        ep = _EmbedParams(self._fptr(pe.proj.weight), self._fptr(pe.proj.bias), self._fptr(pe.channel_embed.weight),
+        ce_ptr = self._ce_override.data_ptr() if getattr(self, "_ce_override", None) is not None else \
+            self._fptr(pe.channel_embed.weight)
+        ep = _EmbedParams(self._fptr(pe.proj.weight), self._fptr(pe.proj.bias), ce_ptr,
                           self._fptr(pe.channel_emb_proxies) if has_prox else None, self._fptr(fe.cls_token),
                           self._fptr(fe.pos_embed), pos_map.data_ptr() if pos_map is not None else None)
         sp = scal.data_ptr()
@@ -717,6 +763,7 @@ class DiChaViT(nn.Module):
         if reducer:
             reducer.ready("embed", flush=True)
             reducer.finish()
+        self._last_gflat = gflat  # FusedAdamW consumes the flat buffer directly
         grads = []
         for p, off, n in self._layout:
             grads.append(gflat[off:off + n].view(p.shape) if p.requires_grad else None)

@@ -98,6 +98,15 @@ int dcv_colsum_bf16(const void* a, float* out, int M, int N, int lda, void* stre
 /* dst(bf16)[i] = src(fp32)[i]: the per-step bf16 copy of the flat parameter buffer. */
 int dcv_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 
+/* Fused AdamW over flat fp32 buffers of n elements (n % 4 == 0): timm/torch AdamW semantics of reference
+ * optimizers.py:20-21 (decoupled weight decay, bias correction with `step` counted from 1).  p_bf16 (nullable):
+ * also refreshes the bf16 operand copy.  clip (nullable): device float[2] = {sum of squared gradients, max_norm};
+ * gradients are scaled by min(1, max_norm / (sqrt(sumsq) + 1e-6)) as torch clip_grad_norm_ (trainer.py:1003-1004). */
+int dcv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* clip, void* stream);
+/* out[0] += sum_i g[i]^2 (n % 4 == 0; caller zeroes out) */
+int dcv_sumsq_f32(const float* g, long long n, float* out, void* stream);
+
 /* C[M,N] = (accumulate ? C : 0) + op(A) op(B) (+ bias[N]); tiny fp32 SIMT GEMM used for the
  * bicubic positional-embedding resample (dichavit.py:518-552, a fixed linear map) and the
  * classifier head (dichavit.py:801,855).  transA: A stored [K,M]; transB: B stored [N,K]. */

@@ -176,6 +176,42 @@ def dcs_select(channel_embed: torch.Tensor, temp: float, mode: str = "lowest_cos
     return c_new, anchor, idx
 
 
+def leave_one_out_channel_tokens(weight: torch.Tensor, mapper: Dict[str, Sequence[int]], chunk_name: str,
+                                 training_chunks: str, new_channel_init: str,
+                                 channel_map: Optional[Dict[int, int]] = None) -> torch.Tensor:
+    """dichavit.py:219-374 (eval only, `training_chunks` given): channel tokens [C_in, D] of the chunk where every
+    channel that was not seen in training gets a token synthesised from training channels.  Modes that need the
+    `bank` attribute (dynamic_input_corr_*) are not restated: nothing in the reference ever sets it."""
+    training_channels = [c for ch in training_chunks.split("_") for c in mapper[ch]]
+    chs_not_seen = [c for c in training_channels if c not in mapper[chunk_name]]
+    ch_banks = chs_not_seen if "not_in_chunk" in new_channel_init else training_channels
+    rows, cur = [], 0
+    for c in mapper[chunk_name]:
+        if c in training_channels:
+            rows.append(weight[c][None])
+            continue
+        n = len(ch_banks)
+        if new_channel_init in ("avg_2", "avg_2_not_in_chunk"):
+            param = weight[[ch_banks[cur], ch_banks[(cur + 1) % n]]].mean(dim=0, keepdim=True)
+        elif new_channel_init in ("avg_3", "avg_3_not_in_chunk"):
+            param = weight[[ch_banks[cur], ch_banks[(cur + 1) % n], ch_banks[(cur + 2) % n]]].mean(dim=0, keepdim=True)
+        elif new_channel_init == "replicate":
+            param = weight[ch_banks[cur]][None]
+        elif new_channel_init == "zero":
+            param = torch.zeros_like(weight[0])[None]
+        elif new_channel_init == "random":
+            param = weight[c][None]
+        elif new_channel_init == "fixed_input_corr":
+            if channel_map is None:
+                raise ValueError("provide a channel_map (dict)!")
+            param = weight[channel_map[c]][None]
+        else:
+            raise ValueError(f"Invalid new_channel_init: '{new_channel_init}'")
+        cur = (cur + 1) % n
+        rows.append(param)
+    return torch.cat(rows, dim=0)
+
+
 # ---------------------------------------------------------------------------------------------
 # losses
 # ---------------------------------------------------------------------------------------------
@@ -282,7 +318,7 @@ class OracleOutput:
 
 def forward(x: torch.Tensor, p: Dict[str, torch.Tensor], cfg: OracleConfig, channels: Sequence[int],
             training: bool, has_head: bool, indices: Optional[Sequence[int]] = None,
-            keep_blocks: bool = False) -> OracleOutput:
+            keep_blocks: bool = False, channel_embed_override: Optional[torch.Tensor] = None) -> OracleOutput:
     """DiChaViT.forward (dichavit.py:844-861) -> ChannelVisionTransformer.forward (:631-652) ->
     prepare_tokens (:554-629) -> PatchEmbedPerChannel.forward (:110-417).
 
@@ -294,6 +330,8 @@ def forward(x: torch.Tensor, p: Dict[str, torch.Tensor], cfg: OracleConfig, chan
     B, C, H, W = x.shape
     chan_ids = torch.tensor(list(channels), device=x.device)
     channel_embed = p[fe + "patch_embed.channel_embed.weight"][chan_ids]  # dichavit.py:122
+    if channel_embed_override is not None:  # eval-time leave-one-out synthesis, dichavit.py:219-374
+        channel_embed = channel_embed_override
     cur_channels = list(channels)
     if training and cfg.enable_sample:
         if indices is None:

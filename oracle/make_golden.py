@@ -227,6 +227,35 @@ def run_dcs(ref):
     print("dcs: oracle == reference on", sum(len(v) for v in recs.values()), "draws")
 
 
+LOO_MAPPER = {"train": [0, 1, 2, 3, 4], "test": [2, 5, 3, 6]}
+LOO_MODES = ["avg_2", "avg_2_not_in_chunk", "avg_3", "avg_3_not_in_chunk", "replicate", "zero", "random"]
+
+
+def run_leave_one_out(ref):
+    """Eval forward with channels unseen in training (dichavit.py:219-374): reference vs oracle, all modes that do
+    not need the never-set `bank` attribute."""
+    oc = O.OracleConfig(pretrained_model_name="tiny", img_size=32, patch_size=8,
+                        in_channel_names=[f"c{i}" for i in range(7)], num_classes=6, proxy_loss_lambda=0.1,
+                        ortho_loss_v1_lambda=0.5)
+    weights = O.make_weights(oc, True, 61)
+    model = build_reference(ref, oc, LOO_MAPPER, weights)
+    model.eval()
+    x, _ = make_inputs(oc, 3, 4, oc.num_classes, 62)
+    first = importlib.import_module("helper_classes.first_layer_init")
+    rec = {}
+    for mode in LOO_MODES:
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            out = model(x, "test", training_chunks="train", new_channel_init=first.NewChannelLeaveOneOut(mode))
+        ce = O.leave_one_out_channel_tokens(weights["feature_extractor.patch_embed.channel_embed.weight"], LOO_MAPPER,
+                                            "test", "train", mode)
+        with torch.no_grad():
+            oo = O.forward(x, weights, oc, LOO_MAPPER["test"], training=False, has_head=True, channel_embed_override=ce)
+        assert (oo.out - out).abs().max().item() < 1e-5, mode
+        rec[mode] = out.numpy()
+    np.savez_compressed(GOLD / "leave_one_out.npz", **rec)
+    print("leave-one-out: oracle == reference for", LOO_MODES)
+
+
 def run_pos_matrix():
     """bicubic positional resample (dichavit.py:518-552) for the grids in use: oracle == reference."""
     ref_mod = sys.modules["models.dichavit"]
@@ -263,6 +292,8 @@ def main():
         run_dcs(ref)
     if not only or "pos" in only:
         run_pos_matrix()
+    if not only or "loo" in only:
+        run_leave_one_out(ref)
 
 
 if __name__ == "__main__":

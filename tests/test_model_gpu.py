@@ -217,3 +217,55 @@ def test_so2sat_shape_all_channel_counts():
         assert abs(m.last_losses["tdl"].item() - oo.tdl.item()) <= LOSS_TOL * abs(oo.tdl.item()) + 1e-7, cs
         assert abs(m.last_losses["cdl"].item() - oo.cdl.item()) <= LOSS_TOL * abs(oo.cdl.item()) + 1e-7, cs
         assert torch.isfinite(out).all()
+
+
+def test_eval_leave_one_out_channel_synthesis():
+    """eval forward on a chunk with channels unseen in training, every supported new_channel_init,
+    against the golden outputs of the reference module."""
+    from oracle.make_golden import LOO_MAPPER, LOO_MODES
+
+    g = load_golden("leave_one_out")
+    oc = O.OracleConfig(pretrained_model_name="tiny", img_size=32, patch_size=8,
+                        in_channel_names=[f"c{i}" for i in range(7)], num_classes=6, proxy_loss_lambda=0.1,
+                        ortho_loss_v1_lambda=0.5)
+    weights = O.make_weights(oc, True, 61)
+    x, _ = make_inputs(oc, 3, 4, oc.num_classes, 62)
+    m = build_cuda_model(oc, LOO_MAPPER, weights).eval()
+    with torch.inference_mode():
+        for mode in LOO_MODES:
+            out = m(x.cuda(), "test", training_chunks="train", new_channel_init=mode)
+            assert isinstance(out, torch.Tensor)
+            assert rel_l2(out, torch.from_numpy(g[mode])) < ACT_TOL, mode
+        # all channels seen: plain lookup
+        x5, _ = make_inputs(oc, 2, 5, oc.num_classes, 63)
+        out = m(x5.cuda(), "train", training_chunks="train", new_channel_init="avg_2")
+        oo = O.forward(x5, weights, oc, LOO_MAPPER["train"], training=False, has_head=True)
+        assert rel_l2(out, oo.out) < ACT_TOL
+
+
+def test_fused_adamw_matches_torch():
+    """the flat-buffer AdamW kernel == torch.optim.AdamW (the reference's optimizer semantics),
+    with and without global-norm clipping, over three steps."""
+    from diverse_channel_vit_b200.optim import FusedAdamW
+
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["tiny_jumpcp"]
+    weights = O.make_weights(oc, has_head, wseed)
+    x, y = make_inputs(oc, B, 8, oc.num_classes, iseed)
+    for clip in (None, 0.5):
+        ma, mb = build_cuda_model(oc, mapper, weights), build_cuda_model(oc, mapper, weights)
+        oa = FusedAdamW(ma, lr=1e-3, weight_decay=0.05, clip_grad_norm=clip)
+        ob = torch.optim.AdamW(mb.parameters(), lr=1e-3, weight_decay=0.05)
+        for _ in range(3):
+            cuda_step(ma, x.cuda(), y.cuda(), chunk, has_head, xlam)
+            # identical gradients for both optimisers (the kernels' atomics make two runs differ in the last bits,
+            # which Adam's m / sqrt(v) amplifies wherever a gradient is ~0)
+            for pa, pb in zip(ma.parameters(), mb.parameters()):
+                pb.grad = None if pa.grad is None else pa.grad.detach().clone()
+            oa.step()
+            if clip is not None:
+                torch.nn.utils.clip_grad_norm_([p for p in mb.parameters() if p.grad is not None], clip)
+            ob.step()
+        for (ka, pa), (kb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            if pb.grad is None:
+                continue
+            assert rel_l2(pa, pb) < 1e-5, (clip, ka, rel_l2(pa, pb))

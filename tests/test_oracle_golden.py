@@ -117,3 +117,36 @@ def test_tdl_single_channel_edge():
     f = torch.nn.functional.normalize(y, dim=-1)
     pos = ((f.sum(1) ** 2).sum(-1) - 5) / (5 * 4 + 1e-6)
     assert abs(v.item() - pos.mean().item()) < 1e-5
+
+
+def test_leave_one_out_matches_reference():
+    """Eval-time channel-token synthesis for channels unseen in training (dichavit.py:219-374)."""
+    from oracle.make_golden import LOO_MAPPER, LOO_MODES
+
+    g = load_golden("leave_one_out")
+    oc = O.OracleConfig(pretrained_model_name="tiny", img_size=32, patch_size=8,
+                        in_channel_names=[f"c{i}" for i in range(7)], num_classes=6, proxy_loss_lambda=0.1,
+                        ortho_loss_v1_lambda=0.5)
+    weights = O.make_weights(oc, True, 61)
+    x, _ = make_inputs(oc, 3, 4, oc.num_classes, 62)
+    w = weights["feature_extractor.patch_embed.channel_embed.weight"]
+    for mode in LOO_MODES:
+        ce = O.leave_one_out_channel_tokens(w, LOO_MAPPER, "test", "train", mode)
+        with torch.no_grad():
+            oo = O.forward(x, weights, oc, LOO_MAPPER["test"], training=False, has_head=True, channel_embed_override=ce)
+        np.testing.assert_allclose(oo.out.numpy(), g[mode], rtol=1e-4, atol=2e-5)
+    # host-side mirror in the drop-in module produces the same token matrix
+    from diverse_channel_vit_b200.dichavit import dichavit
+    from tests.util import ref_cfg
+
+    m = dichavit(ref_cfg(oc), mapper=LOO_MAPPER)
+    m.load_state_dict({k: weights[k] for k in m.state_dict()})
+    pe = m.feature_extractor.patch_embed
+    for mode in LOO_MODES:
+        got = pe.leave_one_out_tokens("test", "train", mode)
+        assert torch.equal(got, O.leave_one_out_channel_tokens(w, LOO_MAPPER, "test", "train", mode))
+    assert pe.leave_one_out_tokens("train", "train", None) is None
+    with pytest.raises(ValueError):
+        pe.leave_one_out_tokens("test", "train", "dynamic_input_corr_1")
+    with pytest.raises(ValueError):
+        pe.leave_one_out_tokens("test", "train", "nonsense")
