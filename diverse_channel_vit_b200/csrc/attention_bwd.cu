@@ -55,7 +55,7 @@ struct AttnBwdParams {
 //       | lse2 / delta of the query tile x2 stages (TMA bulk copies riding on the Q/dO barrier)
 constexpr int kStatBytes = 2 * kTq * 4;  // 128 lse2 + 128 delta
 constexpr int kBwdSmem = 2 * kTile16K + 4 * kTile16K + 2 * kTile16K + 2 * kTile16K + 2 * kStatBytes + 1024 + 256;
-constexpr int kBwdThreads = 320;
+constexpr int kBwdThreads = 448;  // 8 compute warps + TMA warp + MMA warp + 4 dQ-drain warps
 
 __device__ __forceinline__ void wg_barrier(int g) {  // named barrier 1 + g, the 128 threads of warpgroup g
   asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
@@ -118,7 +118,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     mbar_init(p_ready, 256);
     mbar_init(ds_ready, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 256);
+    mbar_init(dq_empty, 128);  // the four drain warps
     mbar_init(dkv_full, 1);
     fence_barrier_init();
   }
@@ -149,16 +149,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
   } else if (warp == 9) {
     // ------------------------------------- MMA issuer -------------------------------------
-    if (lane == 0) {
+    // The whole warp walks the loop (all lanes wait on the barriers) and ONE elected lane issues the MMAs /
+    // commits inside warp-uniform control flow: under `if (lane == 0)` the compiler has to assume divergent
+    // operands and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop, which made the
+    // single issuing thread -- not the tensor pipe -- the bottleneck of this kernel.
+    {
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
-      constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);   // dV, dK : A K-major, B MN-major
+      constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);   // dV, dK : A (TMEM) K-major, B MN-major
       constexpr uint32_t id_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ     : A MN-major, B MN-major
       const uint64_t dK_k = make_desc_kmajor(smem_u32(sK));
       const uint64_t dV_k = make_desc_kmajor(smem_u32(sV));
       const uint64_t dK_mn = make_desc_mnmajor(smem_u32(sK), kTile16K);
+      const uint64_t dS_mn = make_desc_mnmajor(smem_u32(sdS), kTile16K);
       const uint64_t dS_k0 = make_desc_kmajor(smem_u32(sdS));
       const uint64_t dS_k1 = make_desc_kmajor(smem_u32(sdS + kTile16K));
-      const uint64_t dS_mn = make_desc_mnmajor(smem_u32(sdS), kTile16K);
 
       mbar_wait(kv_full, 0);
       mbar_wait(&qdo_full[0], 0);
@@ -166,24 +170,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       {
         const uint64_t dQ_k = make_desc_kmajor(smem_u32(sQ));
         const uint64_t dO_k = make_desc_kmajor(smem_u32(sdO));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tS, dK_k + 2 * k, dQ_k + 2 * k, id_s, k ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < 4; ++k) umma_ss(tS, dK_k + 2 * k, dQ_k + 2 * k, id_s, k ? 1u : 0u);
+          umma_commit(s_full);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dO_k + 2 * k, id_s, k ? 1u : 0u);
-        umma_commit(dp_full);
+          for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dO_k + 2 * k, id_s, k ? 1u : 0u);
+          umma_commit(dp_full);
+        }
+        __syncwarp();
       }
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         const uint64_t dQ_mn = make_desc_mnmajor(smem_u32(sQ + st * kTile16K), kTile16K);
         const uint64_t dO_mn = make_desc_mnmajor(smem_u32(sdO + st * kTile16K), kTile16K);
+        const uint32_t acc = i ? 1u : 0u;
         // dV += P^T dO_i  (A = P^T from TMEM: 16 q per K step = 8 packed columns)
         TL(0, i, 0);
         mbar_wait(p_ready, i & 1);
         tc_fence_after();
         TL(0, i, 1);
+        if (elect_one()) {
+          umma_ts(tdV, tP, dO_mn, id_kv, acc);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_ts(tdV, tP + 8 * k, dO_mn + 128 * k, id_kv, (i | k) ? 1u : 0u);
+          for (int k = 1; k < 8; ++k) umma_ts(tdV, tP + 8 * k, dO_mn + 128 * k, id_kv, 1u);
+        }
+        __syncwarp();
         // S^T of the next query tile may overwrite tS now (phase A of tile i has consumed it)
         uint64_t dOn_k = 0;
         if (i + 1 < n_q) {
@@ -192,36 +204,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           tc_fence_after();
           const uint64_t dQn_k = make_desc_kmajor(smem_u32(sQ + st1 * kTile16K));
           dOn_k = make_desc_kmajor(smem_u32(sdO + st1 * kTile16K));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, dK_k + 2 * k, dQn_k + 2 * k, id_s, k ? 1u : 0u);
-          umma_commit(s_full);
+            for (int k = 0; k < 4; ++k) umma_ss(tS, dK_k + 2 * k, dQn_k + 2 * k, id_s, k ? 1u : 0u);
+            umma_commit(s_full);
+          }
+          __syncwarp();
         }
         // dK += dS^T Q_i ; dQ_i = dS K
         TL(0, i, 2);
         mbar_wait(ds_ready, i & 1);
         tc_fence_after();
         TL(0, i, 3);
+        if (elect_one()) {
+          umma_ss(tdK, dS_k0, dQ_mn, id_kv, acc);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tdK, (k < 4 ? dS_k0 : dS_k1) + 2 * (k & 3), dQ_mn + 128 * k, id_kv, (i | k) ? 1u : 0u);
+          for (int k = 1; k < 8; ++k)
+            umma_ss(tdK, (k < 4 ? dS_k0 : dS_k1) + 2 * (k & 3), dQ_mn + 128 * k, id_kv, 1u);
+        }
+        __syncwarp();
         if (i > 0) {  // the compute warpgroups have drained dQ_{i-1} out of TMEM
           mbar_wait(dq_empty, (i - 1) & 1);
           tc_fence_after();
         }
         TL(0, i, 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_ss(tdQ, dS_mn + 128 * k, dK_mn + 128 * k, id_dq, k ? 1u : 0u);
-        umma_commit(dq_full);
-        umma_commit(&qdo_empty[st]);
-        if (i + 1 < n_q) {
+          for (int k = 0; k < 8; ++k) umma_ss(tdQ, dS_mn + 128 * k, dK_mn + 128 * k, id_dq, k ? 1u : 0u);
+          umma_commit(dq_full);
+          umma_commit(&qdo_empty[st]);
+          if (i + 1 < n_q) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dOn_k + 2 * k, id_s, k ? 1u : 0u);
-          umma_commit(dp_full);
+            for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dOn_k + 2 * k, id_s, k ? 1u : 0u);
+            umma_commit(dp_full);
+          }
         }
+        __syncwarp();
         TL(0, i, 5);
       }
-      umma_commit(dkv_full);
+      if (elect_one()) umma_commit(dkv_full);
+      __syncwarp();
     }
+  } else if (warp >= 10) {
+    // ------------------------------------ dQ drain warps ------------------------------------
+    // dQ_i (128 queries x 64) : TMEM -> two swizzled [128][32] fp32 boxes in smem -> TMA reduce-add into the
+    // [B,H,L,64] accumulator.  Off the critical path of the compute warpgroups.
+    const int q4 = warp & 3;  // TMEM lane quadrant (warps 10..13 -> quadrants 2,3,0,1)
+    const int r = q4 * 32 + lane;
+    const int tid_d = threadIdx.x - 320;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    const uint32_t sdQ0 = smem_u32(sdQ), sdQ1 = smem_u32(sdQ + kTile16K);
+    for (int i = 0; i < n_q; ++i) {
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      uint32_t q0r[32], q1r[32];
+      tmem_ld32(tdQ + lane_base, q0r);
+      tmem_ld32(tdQ + lane_base + 32, q1r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+      if (tid_d == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous reduce has read the boxes
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        st_shared_v4(sdQ0 + sw128_offset(r, v), q0r[4 * v], q0r[4 * v + 1], q0r[4 * v + 2], q0r[4 * v + 3]);
+        st_shared_v4(sdQ1 + sw128_offset(r, v), q1r[4 * v], q1r[4 * v + 1], q1r[4 * v + 2], q1r[4 * v + 3]);
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      if (tid_d == 0) {
+        tma_reduce_add_3d(&map_dq, sdQ, 0, i * kTq, b * p.H + h);
+        tma_reduce_add_3d(&map_dq, sdQ + kTile16K, 32, i * kTq, b * p.H + h);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (tid_d == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reduces fully performed
   } else {
     // --------------------------------- compute warpgroups ---------------------------------
     const int g = warp >> 2;                  // column half
@@ -233,28 +290,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const bool kv_tail = kv0 + kTk > p.L;     // uniform: only the last key tile has masked rows
     const uint32_t sdS_g = smem_u32(sdS + g * kTile16K);
     const uint32_t sdQ_g = smem_u32(sdQ + g * kTile16K);
-
-    auto drain_dq = [&](int i) {
-      // dQ_i columns [32g, 32g+32): TMEM -> swizzled smem box -> TMA reduce-add into dq_acc
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      uint32_t qreg[32];
-      tmem_ld32(tdQ + lane_base + g * 32, qreg);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_empty);
-      if (tid_g == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous reduce has read sdQ_g
-      wg_barrier(g);
-#pragma unroll
-      for (int v = 0; v < 8; ++v)
-        st_shared_v4(sdQ_g + sw128_offset(r, v), qreg[4 * v], qreg[4 * v + 1], qreg[4 * v + 2], qreg[4 * v + 3]);
-      fence_proxy_async_smem();
-      wg_barrier(g);
-      if (tid_g == 0) {
-        tma_reduce_add_3d(&map_dq, sdQ + g * kTile16K, g * 32, i * kTq, b * p.H + h);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    };
 
     for (int i = 0; i < n_q; ++i) {
       // lse2 / delta of this warpgroup's 64 queries (smem, broadcast reads)
@@ -302,9 +337,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_arrive(p_ready);
       TL(1 + g, i, 2);
 
-      // ---- drain dQ_{i-1} while the MMA warp works on dV_i / S_{i+1} ----
-      if (i > 0) drain_dq(i - 1);
-
       // ---- phase B: dS^T = P^T o (dP^T - delta[q])   (softmax scale folded into dK / dQ epilogues) ----
       TL(1 + g, i, 3);
       mbar_wait(dp_full, i & 1);
@@ -337,8 +369,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_arrive(ds_ready);
       TL(1 + g, i, 5);
     }
-    drain_dq(n_q - 1);
-
     // ---- epilogue: dK (x scale) and dV rows of this key tile; warpgroup g writes d columns [32g, 32g+32) ----
     mbar_wait(dkv_full, 0);
     tc_fence_after();
@@ -364,7 +394,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         }
       }
     }
-    if (tid_g == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reduces fully performed
   }
 
   tc_fence_before();
