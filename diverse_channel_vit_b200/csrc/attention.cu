@@ -97,7 +97,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    // whole warp walks the loop; one elected lane issues MMAs / commits inside warp-uniform control flow (under
+    // `if (lane == 0)` every UTCHMMA gets wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop)
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(kTq, kTk, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kTq, kHd, 0, 1);  // B = V, MN-major
       const uint64_t dq = make_desc_kmajor(smem_u32(sQ));
@@ -106,9 +108,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       tc_fence_after();
       {
         const uint64_t dk = make_desc_kmajor(smem_u32(sK));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % kFwdStages;
@@ -116,20 +121,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         const uint64_t dv = make_desc_mnmajor(smem_u32(sV + st * (kTk * kHd * 2)), 64 * 128);
+        const uint32_t acc = j ? 1u : 0u;
+        if (elect_one()) {
+          umma_ts(tO, tP, dv, idesc_pv, acc);
 #pragma unroll
-        for (int k = 0; k < kTk / 16; ++k) umma_ts(tO, tP + 8 * k, dv + 128 * k, idesc_pv, (j | k) ? 1u : 0u);
-        umma_commit(&kv_empty[st]);
+          for (int k = 1; k < kTk / 16; ++k) umma_ts(tO, tP + 8 * k, dv + 128 * k, idesc_pv, 1u);
+          umma_commit(&kv_empty[st]);
+        }
+        __syncwarp();
         if (j + 1 < n_kv) {
           const int st1 = (j + 1) % kFwdStages;
           mbar_wait(&kv_full[st1], ((j + 1) / kFwdStages) & 1);
           tc_fence_after();
           const uint64_t dk = make_desc_kmajor(smem_u32(sK + st1 * (kTk * kHd * 2)));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-          umma_commit(s_full);  // also certifies that PV_j has completed: P and O are quiescent
+            for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+            umma_commit(s_full);  // also certifies that PV_j has completed: P and O are quiescent
+          }
         } else {
-          umma_commit(o_full);
+          if (elect_one()) umma_commit(o_full);
         }
+        __syncwarp();
       }
     }
   } else {

@@ -189,7 +189,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    // whole warp walks the loop, one elected lane issues inside warp-uniform control flow (avoids the per-UTCHMMA
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall the compiler emits under `if (lane == 0)`)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, kBMn ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -205,17 +207,20 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t da = make_desc_kmajor(smem_u32(smem_a + stage * (kBM * kBK * 2)));
           const uint32_t sb_addr = smem_u32(smem_b + stage * (BN * kBK * 2));
           const uint64_t db = kBMn ? make_desc_mnmajor(sb_addr, 64 * 128) : make_desc_kmajor(sb_addr);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
+          const uint32_t acc0 = kb ? 1u : 0u;
+          if (elect_one()) {
             // K-major: +32 bytes per 16-element K step inside the swizzle atom (encoded >> 4);
             // MN-major: 16 reduction rows = 2048 bytes
-            umma_ss(d_tmem, da + 2 * k, db + (kBMn ? 128 : 2) * k, idesc, (kb | k) ? 1u : 0u);
+            umma_ss(d_tmem, da, db, idesc, acc0);
+#pragma unroll
+            for (int k = 1; k < kBK / 16; ++k) umma_ss(d_tmem, da + 2 * k, db + (kBMn ? 128 : 2) * k, idesc, 1u);
+            if (CM > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
+            else umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
           }
-          if (CM > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -556,7 +561,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {
         constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
@@ -565,15 +570,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint64_t da = make_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes), p.lbo_a, p.sbo);
           const uint64_t db = make_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), p.lbo_b, p.sbo);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
+          const uint32_t acc0 = mb ? 1u : 0u;
+          if (elect_one()) {  // one elected lane inside warp-uniform control flow (no UTCHMMA waterfall)
             // 16 reduction rows = 2 swizzle atoms = 2048 bytes (encoded >> 4 = 128)
-            umma_ss(tmem_base, da + 128 * k, db + 128 * k, idesc, (mb | k) ? 1u : 0u);
+            umma_ss(tmem_base, da, db, idesc, acc0);
+#pragma unroll
+            for (int k = 1; k < kBK / 16; ++k) umma_ss(tmem_base, da + 128 * k, db + 128 * k, idesc, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (mb == num_mb - 1) umma_commit(tmem_full);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tmem_full);
       }
     } else if (warp >= 4) {
       // epilogue: 32-column fp32 chunks -> swizzled smem -> TMA reduce-add (split-K) or TMA store
