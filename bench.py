@@ -262,6 +262,7 @@ def ours(args, wname):
     set_seeds(2025, True)
     model = dichavit(model_cfg(w), mapper={"train": list(range(w["channels"]))}).to(dev)
     model.train()
+    model.direct_grad = True  # gradients land in .grad as views of one flat buffer, no per-tensor autograd nodes
     if world > 1:
         model.enable_data_parallel()
     from diverse_channel_vit_b200.optim import FusedAdamW

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "host.h"
@@ -68,6 +69,38 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Tensor maps are pure functions of (pointer, geometry): the same ~60 maps recur every training step, so encoded
+// descriptors are cached per host thread (cuTensorMapEncodeTiled costs ~1 us, several per launch).
+struct TmapKey {
+  const void* ptr;
+  uint64_t d0, d1, d2, s1, s2;
+  uint32_t b0, b1, b2, kind;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && b0 == o.b0 &&
+           b1 == o.b1 && b2 == o.b2 && kind == o.kind;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {k.d0, k.d1, k.d2, k.s1, k.s2, (uint64_t)k.b0 << 32 | k.b1, (uint64_t)k.b2 << 32 | k.kind})
+      h = (h ^ v) * 0x100000001B3ull;
+    return static_cast<size_t>(h);
+  }
+};
+static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> g_tmap_cache;
+
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  auto it = g_tmap_cache.find(k);
+  if (it == g_tmap_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+static void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(k, m);
+}
+
 static EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -82,6 +115,8 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer) {
+  const TmapKey key{ptr, inner, outer, 0, row_stride_bytes, 0, box_inner, box_outer, 0, 1};
+  if (tmap_lookup(key, m)) return 0;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_bytes & 15))
@@ -97,11 +132,14 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
   if (r != CUDA_SUCCESS)
     return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(2d %llux%llu box %ux%u) failed: %d",
                      (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer, (int)r);
+  tmap_store(key, *m);
   return 0;
 }
 
 int make_tmap_2d(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer) {
+  const TmapKey key{ptr, inner, outer, 0, row_stride_bytes, 0, box_inner, box_outer, 0, is_f32 ? 2u : 3u};
+  if (tmap_lookup(key, m)) return 0;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_bytes & 15))
@@ -117,11 +155,14 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t inner, u
   if (r != CUDA_SUCCESS)
     return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(2d %s %llux%llu box %ux%u) failed: %d", is_f32 ? "f32" : "bf16",
                      (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer, (int)r);
+  tmap_store(key, *m);
   return 0;
 }
 
 int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  const TmapKey key{ptr, d0, d1, d2, stride1_bytes, stride2_bytes, box0, box1, box2, 4};
+  if (tmap_lookup(key, m)) return 0;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15))
@@ -134,11 +175,14 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  tmap_store(key, *m);
   return 0;
 }
 
 int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  const TmapKey key{ptr, d0, d1, d2, stride1_bytes, stride2_bytes, box0, box1, box2, 5};
+  if (tmap_lookup(key, m)) return 0;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15))
@@ -151,6 +195,7 @@ int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(3d f32) failed: %d", (int)r);
+  tmap_store(key, *m);
   return 0;
 }
 

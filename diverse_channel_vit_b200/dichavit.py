@@ -429,6 +429,10 @@ class DiChaViT(nn.Module):
         self._pg = None
         self._comm_stream = None
         self.last_losses: Dict[str, torch.Tensor] = {}
+        self._plan_cache: Dict[tuple, dict] = {}
+        self._bp_cache = None
+        self.direct_grad = False  # see _DiChaViTFn.backward
+        self._grad_anchor: Optional[torch.Tensor] = None
         self._arena_bytes: Dict[tuple, int] = {}   # forward arena size of the full-channel plan per input shape
         self._ws_bytes: Dict[tuple, int] = {}      # backward workspace high-water mark per input shape
 
@@ -530,7 +534,12 @@ class DiChaViT(nn.Module):
             if self._ce_override is not None:
                 gid = torch.arange(cs, dtype=torch.int32, device=x.device)  # rows of the synthesised token matrix
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p, _, _ in self._layout)
-        params = [p for p, _, _ in self._layout]
+        if self.direct_grad and need_grad:
+            if self._grad_anchor is None or self._grad_anchor.device != x.device:
+                self._grad_anchor = torch.zeros((), device=x.device, requires_grad=True)
+            params = [self._grad_anchor]  # one differentiable input keeps the node in the graph
+        else:
+            params = [p for p, _, _ in self._layout]
         out, extra = _DiChaViTFn.apply(self, x, cs, idx, gid, need_grad, *params)
         if self.training:
             return out, extra
@@ -538,6 +547,15 @@ class DiChaViT(nn.Module):
 
     # ------------------------------------------------------------------ engine
     def _plan(self, B: int, cs: int, H: int, W: int, keep: bool):
+        key = (B, cs, H, W, keep)
+        hit = self._plan_cache.get(key)
+        if hit is not None:
+            return hit
+        pl = self._plan_build(B, cs, H, W, keep)
+        self._plan_cache[key] = pl
+        return pl
+
+    def _plan_build(self, B: int, cs: int, H: int, W: int, keep: bool):
         fe = self.feature_extractor
         P, D, heads = fe.patch_size, self.dim, fe.num_heads
         N = (H // P) * (W // P)
@@ -605,21 +623,41 @@ class DiChaViT(nn.Module):
                           sp, sp + 4, sp + 8)
         return dims, ecfg, ep, acts, pos_map
 
+    def _block_param_structs(self):
+        """ctypes parameter structs of every block (pointers into the flat fp32 / bf16 buffers), and the element
+        offsets of every block's gradient tensors inside a flat gradient buffer; rebuilt only after a re-flatten."""
+        key = (self._flat.data_ptr(), self._bflat.data_ptr())
+        if self._bp_cache is None or self._bp_cache[0] != key:
+            structs, goffs = [], []
+            for b in self.feature_extractor.blocks:
+                structs.append(_BlockParams(
+                    self._fptr(b.norm1.weight), self._fptr(b.norm1.bias), self._fptr(b.attn.qkv.bias),
+                    self._fptr(b.attn.proj.bias), self._fptr(b.norm2.weight), self._fptr(b.norm2.bias),
+                    self._fptr(b.mlp.fc1.bias), self._fptr(b.mlp.fc2.bias), self._bptr(b.attn.qkv.weight),
+                    self._bptr(b.attn.proj.weight), self._bptr(b.mlp.fc1.weight), self._bptr(b.mlp.fc2.weight)))
+                goffs.append([4 * self._off[id(t)] for t in (
+                    b.norm1.weight, b.norm1.bias, b.attn.qkv.weight, b.attn.qkv.bias, b.attn.proj.weight,
+                    b.attn.proj.bias, b.norm2.weight, b.norm2.bias, b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight,
+                    b.mlp.fc2.bias)])
+            self._bp_cache = (key, structs, goffs)
+        return self._bp_cache[1], self._bp_cache[2]
+
     def _block_structs(self, pl, base: int, i: int):
         s = pl["arena"].slots
         keep = pl["keep"]
         k = i if keep else 0
         xin = f"x{i}" if keep else f"x{i % 2}"
         xout = f"x{i + 1}" if keep else f"x{(i + 1) % 2}"
-        b = self.feature_extractor.blocks[i]
-        bp = _BlockParams(self._fptr(b.norm1.weight), self._fptr(b.norm1.bias), self._fptr(b.attn.qkv.bias),
-                          self._fptr(b.attn.proj.bias), self._fptr(b.norm2.weight), self._fptr(b.norm2.bias),
-                          self._fptr(b.mlp.fc1.bias), self._fptr(b.mlp.fc2.bias), self._bptr(b.attn.qkv.weight),
-                          self._bptr(b.attn.proj.weight), self._bptr(b.mlp.fc1.weight), self._bptr(b.mlp.fc2.weight))
-        ba = _BlockActs(base + s[xin], base + s[f"u{k}"], base + s[f"mean1_{k}"], base + s[f"rstd1_{k}"],
-                        base + s[f"qkv{k}"], base + s[f"o{k}"], base + s[f"lse{k}"], base + s[f"xmid{k}"],
-                        base + s[f"v{k}"], base + s[f"mean2_{k}"], base + s[f"rstd2_{k}"], base + s[f"h{k}"],
-                        base + s[f"g{k}"], base + s[xout])
+        bp = self._block_param_structs()[0][i]
+        cache = pl.setdefault("acts_cache", {})
+        ba = cache.get((base, i))
+        if ba is None:
+            ba = _BlockActs(base + s[xin], base + s[f"u{k}"], base + s[f"mean1_{k}"], base + s[f"rstd1_{k}"],
+                            base + s[f"qkv{k}"], base + s[f"o{k}"], base + s[f"lse{k}"], base + s[f"xmid{k}"],
+                            base + s[f"v{k}"], base + s[f"mean2_{k}"], base + s[f"rstd2_{k}"], base + s[f"h{k}"],
+                            base + s[f"g{k}"], base + s[xout])
+            if len(cache) < 256:
+                cache[(base, i)] = ba
         return bp, ba, xout
 
     def _run_forward(self, x: torch.Tensor, cs: int, idx, gid, keep: bool):
@@ -730,15 +768,13 @@ class DiChaViT(nn.Module):
         reducer = _GradReducer(self, gflat) if self.grad_allreduce else None
         if reducer:
             reducer.ready("tail", flush=True)
+        goffs = self._block_param_structs()[1]
         bd = _Dims(B, L, D, heads, Fh)
         bws = _BlockWs(wb + w["dh"], wb + w["dv"], wb + w["d_o"], wb + w["dqkv"], wb + w["delta"], wb + w["dq_acc"])
         for i in reversed(range(pl["depth"])):
             bp, ba, _ = self._block_structs(pl, base, i)
-            b = fe.blocks[i]
-            bg = _BlockGrads(gp(b.norm1.weight), gp(b.norm1.bias), gp(b.attn.qkv.weight), gp(b.attn.qkv.bias),
-                             gp(b.attn.proj.weight), gp(b.attn.proj.bias), gp(b.norm2.weight), gp(b.norm2.bias),
-                             gp(b.mlp.fc1.weight), gp(b.mlp.fc1.bias), gp(b.mlp.fc2.weight), gp(b.mlp.fc2.bias))
-            prev_bias = gp(fe.blocks[i - 1].mlp.fc2.bias) if i > 0 else None
+            bg = _BlockGrads(*[gb + o for o in goffs[i]])
+            prev_bias = gb + goffs[i - 1][11] if i > 0 else None
             if i == pl["depth"] - 1:
                 check(lib.dcv_block_bwd_cls(byref(bd), byref(bp), byref(ba), byref(bg), byref(bws),
                                             c_void_p(wb + w["dres_c"]), c_void_p(wb + w["dres_c_b"]),
@@ -764,10 +800,22 @@ class DiChaViT(nn.Module):
             reducer.ready("embed", flush=True)
             reducer.finish()
         self._last_gflat = gflat  # FusedAdamW consumes the flat buffer directly
-        grads = []
-        for p, off, n in self._layout:
-            grads.append(gflat[off:off + n].view(p.shape) if p.requires_grad else None)
-        return grads
+        if self.direct_grad:
+            # skip autograd's 150 AccumulateGrad nodes: .grad of every parameter becomes (or accumulates) a view of the
+            # flat buffer.  Tensor hooks / DDP reducer hooks on the parameters do NOT fire in this mode.
+            views = self._grad_views(gflat)
+            for (p, _, _), v in zip(self._layout, views):
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = v
+                else:
+                    p.grad.add_(v)
+            return None
+        return [v if p.requires_grad else None for (p, _, _), v in zip(self._layout, self._grad_views(gflat))]
+
+    def _grad_views(self, gflat: torch.Tensor):
+        return [gflat[off:off + n].view(p.shape) for p, off, n in self._layout]
 
 
 class _GradReducer:
@@ -855,6 +903,8 @@ class _DiChaViTFn(torch.autograd.Function):
             raise DcvError("backward called on a forward that ran without gradient tracking")
         grads = ctx.module._run_backward(ctx.state, d_out, d_extra)
         ctx.state = None
+        if grads is None:  # direct_grad: gradients were written to .grad, the only input is the anchor scalar
+            return (None, None, None, None, None, None, None)
         return (None, None, None, None, None, None, *grads)
 
 

@@ -26,7 +26,11 @@ class FusedAdamW:
         self._clip = None
 
     def zero_grad(self, set_to_none: bool = True):
-        self.model.zero_grad(set_to_none=set_to_none)
+        if set_to_none:  # nn.Module.zero_grad walks named_parameters(): 0.7 ms of host time per step for 150 tensors
+            for p, _, _ in self.model._layout or [(q, 0, 0) for q in self.model.parameters()]:
+                p.grad = None
+        else:
+            self.model.zero_grad(set_to_none=False)
 
     def _flat_grad(self) -> torch.Tensor:
         m = self.model
