@@ -46,6 +46,12 @@ WORKLOADS = {
     "so2sat": dict(size="small", img=32, patch=8, channels=18, classes=17, batch=128, hcs_temp=0.01, l_cdl=0.001,
                    l_tdl=0.1, gs=0.5, gd=4.0, sample=True,
                    desc="DiChaViT ViT-S/8 So2Sat 18ch 32x32 (<=289 tokens), 128 img/GPU, DCS+CDL+TDL, CE-17"),
+    # BASELINE configs[1]: one optimiser step = three fwd+bwd (one per chunk, batch 64 split 22/21/21), proxy loss
+    "chammi": dict(size="small", img=224, patch=16, channels=12, classes=14, batch=64, hcs_temp=0.1, l_cdl=0.1,
+                   l_tdl=1.0, gs=0.5, gd=2.0, sample=True, temperature=0.07,
+                   chunks={"Allen": ([0, 1, 2], 22), "HPA": ([3, 4, 5, 6], 21), "CP": ([7, 8, 9, 10, 11], 21)},
+                   desc="DiChaViT ViT-S/16 CHAMMI mixed 3/4/5-channel chunks (Allen/HPA/CP, 22+21+21 img), DCS+CDL+TDL, "
+                        "proxy loss, 3 fwd+bwd per optimiser step"),
     "vitb": dict(size="base", img=224, patch=16, channels=8, classes=161, batch=16, hcs_temp=0.1, l_cdl=0.0,
                  l_tdl=0.0, gs=1.0, gd=0.5, sample=False,
                  desc="DiChaViT ViT-B/16 JUMP-CP 8ch full channels (1569 tokens), 16 img/GPU, CE-161"),
@@ -54,7 +60,7 @@ WORKLOADS = {
 
 def model_cfg(w) -> Cfg:
     return Cfg(name="dichavit", pretrained=False, pretrained_model_name=w["size"], in_dim=None, num_classes=w["classes"],
-               pooling="avg", temperature=0.11111, learnable_temp=False, unfreeze_last_n_layers=-1,
+               pooling="avg", temperature=w.get("temperature", 0.11111), learnable_temp=False, unfreeze_last_n_layers=-1,
                unfreeze_first_layer=True, init_first_layer=None, reset_last_n_unfrozen_layers=False,
                enable_sample=w["sample"], in_channel_names=[f"c{i}" for i in range(w["channels"])],
                new_channel_inits=None, use_channelvit_channels=True, patch_size=w["patch"],
@@ -260,7 +266,9 @@ def ours(args, wname):
 
     B = w["batch"]
     set_seeds(2025, True)
-    model = dichavit(model_cfg(w), mapper={"train": list(range(w["channels"]))}).to(dev)
+    chunks = w.get("chunks")
+    mapper = {k: v[0] for k, v in chunks.items()} if chunks else {"train": list(range(w["channels"]))}
+    model = dichavit(model_cfg(w), mapper=mapper).to(dev)
     model.train()
     model.direct_grad = True  # gradients land in .grad as views of one flat buffer, no per-tensor autograd nodes
     if world > 1:
@@ -269,7 +277,8 @@ def ours(args, wname):
 
     opt = FusedAdamW(model, lr=4e-4, weight_decay=0.04)  # timm/torch AdamW semantics, one launch on the flat buffers
     gen = torch.Generator(device="cpu").manual_seed(2025 + rank)
-    x_host = torch.randn(B, w["channels"], w["img"], w["img"], generator=gen).pin_memory()
+    max_ch = max(len(v[0]) for v in chunks.values()) if chunks else w["channels"]
+    x_host = torch.randn(B, max_ch, w["img"], w["img"], generator=gen).pin_memory()
     y_host = torch.randint(0, w["classes"], (B,), generator=gen).pin_memory()
     x_dev = x_host.to(dev)
     y_dev = y_host.to(dev)
@@ -279,11 +288,22 @@ def ours(args, wname):
     # > 126 MB L2 flush buffer, written between timed steps is unnecessary here: one step streams several GB
     # of activations (far larger than L2); stated in config.l2.
 
+    from oracle_free_losses import proxy_loss as _proxy_loss  # noqa: E402  (plain torch loss glue of the trainer)
+
     def step(x, y):
         opt.zero_grad(set_to_none=True)
-        out, extra = model(x, "train")
-        loss = F.cross_entropy(out, y) + extra * 1.0  # trainer.py:986-995
-        loss.backward()
+        if chunks:  # trainer.py:846-931: one forward/backward per chunk, one optimiser step
+            off = 0
+            for name, (chs, nb) in chunks.items():
+                xc = x[off:off + nb, :len(chs)].contiguous()
+                out, extra = model(xc, name)
+                loss = _proxy_loss(model.proxies, out, y[off:off + nb], model.scale) + extra * 1.0  # trainer.py:912-914
+                loss.backward()
+                off += nb
+        else:
+            out, extra = model(x, "train")
+            loss = F.cross_entropy(out, y) + extra * 1.0  # trainer.py:986-995
+            loss.backward()
         opt.step()
         return loss
 
@@ -388,43 +408,49 @@ def ours(args, wname):
     prof_dcs = {names[i]: round(msb[i] / K, 4) for i in range(ntags) if cnt[i]}
 
     D = model.dim
-    L = 1 + w["channels"] * (w["img"] // w["patch"]) ** 2
+    npatch = (w["img"] // w["patch"]) ** 2
+    L = 1 + (max_ch if chunks else w["channels"]) * npatch
     depth = len(model.feature_extractor.blocks)
+    # sub-batches of one (full-channel) step: (images, tokens per image)
+    subs = [(nb, 1 + len(chs) * npatch) for chs, nb in chunks.values()] if chunks else [(B, L)]
+    # algorithmic FLOPs per STEP and kernel class for the work actually performed (the last block only
+    # runs one query tile of attention and CLS-row proj / MLP; recomputation of S in the backward is not counted)
+    fl = {"attn_fwd": 0.0, "attn_bwd": 0.0, "gemm_nt": 0.0}
+    for nb, Lc in subs:
+        att = 4.0 * Lc * Lc * D * nb * ((depth - 1) + min(1.0, 128.0 / Lc))
+        fl["attn_fwd"] += att
+        fl["attn_bwd"] += 2.0 * att
+        fl["gemm_nt"] += (depth - 1) * 2.0 * nb * Lc * D * 12 * D + 2.0 * nb * Lc * D * 3 * D + 2.0 * nb * D * 9 * D
+    fl["gemm_nn"] = fl["gemm_nt"]  # dgrad
+    fl["gemm_tn"] = fl["gemm_nt"]  # wgrad
     top = max(prof.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if prof else None
     roof = None
-    # attention launches per step: depth-1 full ones + the last block's CLS-only one (one 128-query tile: the
-    # work actually performed); per-launch average used for the roofline line
-    cls_frac = min(1.0, 128.0 / L)
-    att_scale = ((depth - 1) + cls_frac) / depth
-    tensor_classes = {"attn_bwd": algorithmic_flops_attn(B, L, D, True) * att_scale,
-                      "attn_fwd": algorithmic_flops_attn(B, L, D, False) * att_scale}
-    M = B * L
-    gemm_flops_fwd = 2.0 * M * D * (3 * D + D + 4 * D + 4 * D)  # qkv, proj, fc1, fc2 per block
-    tensor_classes["gemm_nt"] = gemm_flops_fwd / 4.0  # per launch average (4 launches / block)
-    tensor_classes["gemm_nn"] = gemm_flops_fwd / 4.0
-    tensor_classes["gemm_tn"] = gemm_flops_fwd / 4.0
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback"
     traffic = None
     try:
         tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
-        if top in tj and "B" in tj[top] and tj[top].get("L") == L:
+        if top in tj and "B" in tj[top] and tj[top].get("L") == L and not chunks:
             traffic = tj[top]["dram_bytes"] * B / tj[top]["B"]  # ncu capture at another batch size, linear in B
     except Exception:
         pass
-    if top in tensor_classes:
-        per_launch_ms = prof[top]["ms_per_step"] / prof[top]["launches_per_step"]
-        ach = tensor_classes[top] / (per_launch_ms * 1e-3) / 1e12
+    if top in fl:
+        ms_top = prof[top]["ms_per_step"]
+        ach = fl[top] / (ms_top * 1e-3) / 1e12
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_ms": per_launch_ms, "share_of_step": prof[top]["ms_per_step"] / (ms_prof / kp),
-                "note": "full-channel pass (L=%d); algorithmic FLOPs per launch averaged over the %d full launches and the "
-                        "last block's CLS-only launch (one query tile); recompute not counted" % (L, depth - 1)}
+                "avg_launch_ms": ms_top / prof[top]["launches_per_step"],
+                "launches_per_step": prof[top]["launches_per_step"], "share_of_step": ms_top / (ms_prof / kp),
+                "note": "full-channel pass; achieved = algorithmic FLOPs of all launches of this kernel class in one step / "
+                        "their summed CUDA-event time; work actually performed (last block: one query tile, CLS-row "
+                        "proj/MLP); recompute not counted"}
     elif top is not None:
         roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": float(peaks.get("hbm_gbs", 6650.0)),
                 "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
-    attn_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("attn_fwd", "attn_bwd"))
-    attn_tf = depth * (tensor_classes["attn_fwd"] + tensor_classes["attn_bwd"]) / (attn_ms * 1e-3) / 1e12 if attn_ms else None
+    attn_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("attn_fwd", "attn_bwd", "attn_bwd_prep", "attn_bwd_fin"))
+    attn_tf = (fl["attn_fwd"] + fl["attn_bwd"]) / (attn_ms * 1e-3) / 1e12 if attn_ms else None
+    gemm_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("gemm_nt", "gemm_nn", "gemm_tn"))
+    gemm_tf = 3.0 * fl["gemm_nt"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
 
     if rank != 0:
         if world > 1:
@@ -470,13 +496,15 @@ def ours(args, wname):
         "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         "kernel_breakdown_dcs_ms_per_step": dict(sorted(prof_dcs.items(), key=lambda kv: -kv[1])),
         "attn_tflops": attn_tf, "attn_frac_of_peak": (attn_tf / peak_tf) if attn_tf else None,
+        "gemm_tflops": gemm_tf, "gemm_frac_of_peak": (gemm_tf / peak_tf) if gemm_tf else None,
         "cpu_baseline": cpu,
         "torch_eager_gpu": eager,
     }
     # algorithmic model FLOPs of the full-channel step: fwd = 2 T P^2 D + depth (24 L D^2 + 4 L^2 D) + 2 D cls
-    T = L - 1
-    fwd = 2.0 * T * w["patch"] ** 2 * D + depth * (24.0 * L * D * D + 4.0 * L * L * D) + 2.0 * D * w["classes"]
-    line["full_channels"]["model_tflops"] = 3.0 * fwd * B * world / (ms_full / kf * 1e-3) / 1e12
+    fwd = 0.0
+    for nb, Lc in subs:
+        fwd += nb * (2.0 * (Lc - 1) * w["patch"] ** 2 * D + depth * (24.0 * Lc * D * D + 4.0 * Lc * Lc * D) + 2.0 * D * w["classes"])
+    line["full_channels"]["model_tflops"] = 3.0 * fwd * world / (ms_full / kf * 1e-3) / 1e12
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

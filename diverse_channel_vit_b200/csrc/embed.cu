@@ -132,19 +132,31 @@ tdl_sum_kernel(const float* __restrict__ tokens, const float* __restrict__ adden
     acc[k] = make_float4(0, 0, 0, 0);
   }
   float q = 0.f;
-  for (int p = warp; p < N; p += kTdlWarps) {
+  // software pipeline: the next token's loads are in flight while this one is normalised and accumulated
+  auto load_row = [&](int p, float4 (&tv)[NV], float4 (&av)[NV]) {
     const int t = c * N + p;
     const float4* tr = reinterpret_cast<const float4*>(tokens + (static_cast<size_t>(b) * (T + 1) + 1 + t) * D);
     const float4* ar = reinterpret_cast<const float4*>(addend + static_cast<size_t>(t) * D);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      tv[k] = v < nvec ? __ldcs(tr + v) : make_float4(0, 0, 0, 0);
+      av[k] = v < nvec ? __ldg(ar + v) : make_float4(0, 0, 0, 0);
+    }
+  };
+  float4 tv[NV], av[NV], tn[NV], an[NV];
+  if (warp < N) load_row(warp, tv, av);
+  for (int p = warp; p < N; p += kTdlWarps) {
+    const int t = c * N + p;
+    if (p + kTdlWarps < N) load_row(p + kTdlWarps, tn, an);
     float4 y[NV];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nvec) {
-        const float4 tv = tr[v], av = __ldg(ar + v);
-        y[k] = make_float4(tv.x - av.x + bi[k].x, tv.y - av.y + bi[k].y, tv.z - av.z + bi[k].z,
-                           tv.w - av.w + bi[k].w);
+        y[k] = make_float4(tv[k].x - av[k].x + bi[k].x, tv[k].y - av[k].y + bi[k].y, tv[k].z - av[k].z + bi[k].z,
+                           tv[k].w - av[k].w + bi[k].w);
         ss += (y[k].x * y[k].x + y[k].y * y[k].y) + (y[k].z * y[k].z + y[k].w * y[k].w);
       } else {
         y[k] = make_float4(0, 0, 0, 0);
@@ -155,6 +167,8 @@ tdl_sum_kernel(const float* __restrict__ tokens, const float* __restrict__ adden
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       acc[k].x += y[k].x * inv; acc[k].y += y[k].y * inv; acc[k].z += y[k].z * inv; acc[k].w += y[k].w * inv;
+      tv[k] = tn[k];
+      av[k] = an[k];
     }
     q += ss * inv * inv;
     if (lane == 0) rnorm[static_cast<size_t>(b) * T + t] = inv;
