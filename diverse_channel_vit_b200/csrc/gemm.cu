@@ -83,11 +83,18 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 2, 256;" 
 // its own A tile and 1/CM of the shared B tile, multicasting that slice into the shared memory of all CTAs of the
 // cluster: L2 -> SM operand traffic per CTA drops from (128 + BN) to (128 + BN / CM) rows per K step (the L2
 // bandwidth, ~6.3 KB/clk chip-wide, is what caps a 128 x 192 single-CTA tile at ~1 PFLOP/s).
-template <int BN, int EPI, bool kBMn, int CM>
+// MODE 2 (pair MMA, `cta_group::2`): the two CTAs of a cluster compute ONE 256 x BN tile with a single MMA stream
+// issued by the leader CTA; each CTA loads its 128 rows of A and HALF of B into its own shared memory and receives its
+// 128 accumulator rows in its own TMEM.  Per-SM operand inflow per K step drops from (128 + BN) to (128 + BN/2) rows --
+// the measured ~36-45 B/clk/SM L2 -> SM rate is what caps the single-CTA main loop.
+template <int BN, int EPI, bool kBMn, int MODE>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
                const __grid_constant__ CUtensorMap map_in, const GemmNtParams p) {
+  constexpr int CM = MODE == 0 ? 1 : 2;     // CTAs per cluster (consecutive M-tiles of one N-tile)
+  constexpr bool kPair = MODE == 2;          // cta_group::2 MMA
+  static_assert(!(kPair && kBMn), "pair MMA implemented for K-major B only");
   using Cfg = NtCfg<BN, EPI>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = Cfg::kStages;
@@ -136,16 +143,21 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CM);  // released by the MMA warp of every CTA that received the stage
+      // multicast mode: released by the MMA warp of every CTA that received the stage; pair mode: by the leader's
+      // multicast commit only
+      mbar_init(&empty_bar[i], kPair ? 1 : CM);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
       mbar_init(&in_full[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair(tmem_base_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
   if (CM > 1) cluster_sync_all();  // peers' barriers must be initialised before remote arrives / multicast writes
   else __syncthreads();
@@ -162,10 +174,19 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tile_coords(it, m0, n0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sb = smem_b + stage * (BN * kBK * 2);
+          if (kPair) {
+            // both CTAs credit the LEADER's barrier: A tile + half of B from each of them
+            constexpr uint32_t kHalfBytes = (kBM + BN / 2) * kBK * 2;
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kHalfBytes);
+            tma_load_2d_pair(smem_a + stage * (kBM * kBK * 2), &map_a, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * kBK, n0 + crank * (BN / 2));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           // bytes landing in THIS CTA's stage: own A tile + all CM slices of B
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(smem_a + stage * (kBM * kBK * 2), &map_a, &full_bar[stage], kb * kBK, m0);
-          uint8_t* sb = smem_b + stage * (BN * kBK * 2);
           if (kBMn) {
             // B stored [K rows][N cols] (e.g. a weight W[out,in] used as dY*W): MN-major boxes of
             // [64 reduction rows][64 output columns]; a cluster slice is 64/CM reduction rows of every box
@@ -191,8 +212,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------- MMA issuer -------------------------------
     // whole warp walks the loop, one elected lane issues inside warp-uniform control flow (avoids the per-UTCHMMA
     // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall the compiler emits under `if (lane == 0)`)
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, kBMn ? 1 : 0);
+    if (!kPair || crank == 0) {  // pair mode: the leader CTA issues for both
+      constexpr uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, BN, 0, kBMn ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -211,12 +232,20 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (elect_one()) {
             // K-major: +32 bytes per 16-element K step inside the swizzle atom (encoded >> 4);
             // MN-major: 16 reduction rows = 2048 bytes
-            umma_ss(d_tmem, da, db, idesc, acc0);
+            if (kPair) {
+              umma_ss_pair(d_tmem, da, db, idesc, acc0);
 #pragma unroll
-            for (int k = 1; k < kBK / 16; ++k) umma_ss(d_tmem, da + 2 * k, db + (kBMn ? 128 : 2) * k, idesc, 1u);
-            if (CM > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
-            else umma_commit(&empty_bar[stage]);
-            if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
+              for (int k = 1; k < kBK / 16; ++k) umma_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+              umma_commit_pair_mc(&empty_bar[stage], kMcMask);
+              if (kb == num_kb - 1) umma_commit_pair_mc(&tmem_full[as], kMcMask);
+            } else {
+              umma_ss(d_tmem, da, db, idesc, acc0);
+#pragma unroll
+              for (int k = 1; k < kBK / 16; ++k) umma_ss(d_tmem, da + 2 * k, db + (kBMn ? 128 : 2) * k, idesc, 1u);
+              if (CM > 1) umma_commit_mc(&empty_bar[stage], kMcMask);
+              else umma_commit(&empty_bar[stage]);
+              if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -277,7 +306,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (c == kChunks - 1) {  // the whole accumulator tile has been read out
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) {
+          if (kPair && crank != 0) mbar_arrive_remote(&tmem_empty[as], 0);  // the leader's MMA warp waits for both CTAs
+          else mbar_arrive(&tmem_empty[as]);
+        }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
       if (EPI != EPI_DGELU && p.bias != nullptr) {
@@ -463,7 +495,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -631,11 +664,12 @@ struct EpiMaps {
   CUtensorMap out, out2, in;
 };
 
-template <int BN, int EPI, bool kBMn, int CM>
+template <int BN, int EPI, bool kBMn, int MODE>
 static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p, cudaStream_t st) {
   using Cfg = NtCfg<BN, EPI>;
   using ET = EpiTraits<EPI>;
-  auto kern = gemm_nt_kernel<BN, EPI, kBMn, CM>;
+  constexpr int CM = MODE == 0 ? 1 : 2;
+  auto kern = gemm_nt_kernel<BN, EPI, kBMn, MODE>;
   EpiMaps em;
   em.out = em.out2 = em.in = ma;  // placeholders for the maps an epilogue does not use
   if (ET::kTma) {
@@ -679,25 +713,27 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
   return 0;
 }
 
-template <int BN, int CM>
+template <int BN, int MODE>
 static int dispatch_nt_epi(int epi, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtParams& p,
                            cudaStream_t st) {
   if (b_mn) {  // dgrad flavours only
-    switch (epi) {
-      case EPI_BIAS: return launch_nt<BN, EPI_BIAS, true, CM>(ma, mb, p, st);
-      case EPI_DGELU: return launch_nt<BN, EPI_DGELU, true, CM>(ma, mb, p, st);
-      case EPI_F32: return launch_nt<BN, EPI_F32, true, CM>(ma, mb, p, st);
+    if constexpr (MODE != 2) {
+      switch (epi) {
+        case EPI_BIAS: return launch_nt<BN, EPI_BIAS, true, MODE>(ma, mb, p, st);
+        case EPI_DGELU: return launch_nt<BN, EPI_DGELU, true, MODE>(ma, mb, p, st);
+        case EPI_F32: return launch_nt<BN, EPI_F32, true, MODE>(ma, mb, p, st);
+      }
     }
-    return set_error(DCV_ERR_UNSUPPORTED, "gemm_nn: epilogue %d not instantiated", epi);
+    return set_error(DCV_ERR_UNSUPPORTED, "gemm_nn: epilogue %d / mode %d not instantiated", epi, MODE);
   }
   switch (epi) {
-    case EPI_BIAS: return launch_nt<BN, EPI_BIAS, false, CM>(ma, mb, p, st);
-    case EPI_BIAS_GELU: return launch_nt<BN, EPI_BIAS_GELU, false, CM>(ma, mb, p, st);
-    case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID, false, CM>(ma, mb, p, st);
-    case EPI_DGELU: return launch_nt<BN, EPI_DGELU, false, CM>(ma, mb, p, st);
-    case EPI_F32: return launch_nt<BN, EPI_F32, false, CM>(ma, mb, p, st);
+    case EPI_BIAS: return launch_nt<BN, EPI_BIAS, false, MODE>(ma, mb, p, st);
+    case EPI_BIAS_GELU: return launch_nt<BN, EPI_BIAS_GELU, false, MODE>(ma, mb, p, st);
+    case EPI_BIAS_RESID: return launch_nt<BN, EPI_BIAS_RESID, false, MODE>(ma, mb, p, st);
+    case EPI_DGELU: return launch_nt<BN, EPI_DGELU, false, MODE>(ma, mb, p, st);
+    case EPI_F32: return launch_nt<BN, EPI_F32, false, MODE>(ma, mb, p, st);
     case EPI_EMBED:
-      if (CM == 1) return launch_nt<BN, EPI_EMBED, false, 1>(ma, mb, p, st);
+      if constexpr (MODE == 0) return launch_nt<BN, EPI_EMBED, false, 0>(ma, mb, p, st);
       break;
   }
   return set_error(DCV_ERR_INVALID, "gemm_nt: unknown epilogue %d", epi);
@@ -707,6 +743,12 @@ static int dispatch_nt_epi(int epi, bool b_mn, const CUtensorMap& ma, const CUte
 // (qkv 50.2 us without vs 51.8 us with a 2-CTA cluster) -- these GEMMs sit at the HBM ridge, not at the L2 -> SM
 // limit -- so the default stays 1; dcv_debug_set_nt_cluster(2) switches the multicast path on.
 static int g_nt_cluster = 1;
+// 1: K-major-B GEMMs (forward Linear layers) run as cta_group::2 pair MMAs (256 x BN tile per 2-CTA cluster).  Correct
+// on B200, but measured slower at the ViT-S shapes (qkv 61.7 vs 50.7 us, fc1+GELU 126 vs 108 us): with K = 384 the
+// main loop is bounded by shared-memory bandwidth (TMA writes + UMMA operand reads ~ 208 B/clk wanted vs 128 B/clk),
+// which the pair mode reduces by only ~15 % while adding cross-CTA barrier latency.  Off by default
+// (dcv_debug_set_nt_cluster(3) enables it).
+static int g_nt_pair = 0;
 
 // b_mn = false: B is [N][K] (K contiguous);  b_mn = true: B is [K][N] (N contiguous)
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
@@ -721,7 +763,8 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   else if (N % 64 == 0) bn = 64;
   else return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: N=%d must be a multiple of 64", N);
   ProfScope prof(b_mn ? PT_GEMM_NN : (epi == EPI_EMBED ? PT_EMBED_GEMM : PT_GEMM_NT), st);
-  const int cm = (epi == EPI_EMBED || M <= kBM) ? 1 : g_nt_cluster;
+  const bool pair = g_nt_pair && !b_mn && epi != EPI_EMBED && M > kBM && N % 128 == 0;
+  const int cm = pair ? 2 : ((epi == EPI_EMBED || M <= kBM) ? 1 : g_nt_cluster);
   CUtensorMap ma, mb;
   if (int e = make_tmap_bf16_2d(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM)) return e;
   // B boxes are 1/cm of the tile: each CTA of a cluster fetches one slice and multicasts it
@@ -744,21 +787,31 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
     return set_error(DCV_ERR_INVALID, "gemm_nt: EPI_EMBED needs addend, T>0, L>T, M %% T == 0");
   if ((epi == EPI_BIAS_GELU && !out2) || (epi == EPI_BIAS_RESID && !resid) || (epi == EPI_DGELU && !aux) || !out)
     return set_error(DCV_ERR_INVALID, "gemm_nt: missing buffer for epilogue %d", epi);
-  if (cm == 2) {
+  if (pair) {
     switch (bn) {
       case 192: return dispatch_nt_epi<192, 2>(epi, b_mn, ma, mb, p, st);
-      case 128: return dispatch_nt_epi<128, 2>(epi, b_mn, ma, mb, p, st);
-      default: return dispatch_nt_epi<64, 2>(epi, b_mn, ma, mb, p, st);
+      default: return dispatch_nt_epi<128, 2>(epi, b_mn, ma, mb, p, st);
+    }
+  }
+  if (cm == 2) {
+    switch (bn) {
+      case 192: return dispatch_nt_epi<192, 1>(epi, b_mn, ma, mb, p, st);
+      case 128: return dispatch_nt_epi<128, 1>(epi, b_mn, ma, mb, p, st);
+      default: return dispatch_nt_epi<64, 1>(epi, b_mn, ma, mb, p, st);
     }
   }
   switch (bn) {
-    case 192: return dispatch_nt_epi<192, 1>(epi, b_mn, ma, mb, p, st);
-    case 128: return dispatch_nt_epi<128, 1>(epi, b_mn, ma, mb, p, st);
-    default: return dispatch_nt_epi<64, 1>(epi, b_mn, ma, mb, p, st);
+    case 192: return dispatch_nt_epi<192, 0>(epi, b_mn, ma, mb, p, st);
+    case 128: return dispatch_nt_epi<128, 0>(epi, b_mn, ma, mb, p, st);
+    default: return dispatch_nt_epi<64, 0>(epi, b_mn, ma, mb, p, st);
   }
 }
 
-void debug_set_nt_cluster(int cm) { g_nt_cluster = (cm == 2) ? 2 : 1; }
+// cm: 1 = single-CTA tiles, 2 = B multicast in 2-CTA clusters, 3 = cta_group::2 pair MMA for K-major B (default)
+void debug_set_nt_cluster(int cm) {
+  g_nt_cluster = (cm == 2) ? 2 : 1;
+  g_nt_pair = (cm == 3) ? 1 : 0;
+}
 
 template <int BN>
 static int launch_tn(const CUtensorMap& ma, const CUtensorMap& mb, GemmTnParams p, cudaStream_t st) {

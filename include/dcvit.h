@@ -257,7 +257,8 @@ const char* dcv_profile_tag_name(int tag);
 int dcv_profile_start(void);
 int dcv_profile_stop(double* ms_by_tag, long long* launches_by_tag, int ntags);
 
-/* debug: cluster size (1 or 2) of the B-operand TMA multicast in dcv_gemm_nt / dcv_gemm_nn (default 1) */
+/* debug: GEMM cluster mode of dcv_gemm_nt / dcv_gemm_nn: 1 = single-CTA tiles (default), 2 = TMA multicast of the B
+ * operand inside 2-CTA clusters, 3 = cta_group::2 pair MMA (256 x BN tiles) for K-major B */
 void dcv_debug_set_nt_cluster(int cm);
 
 /* debug: clock64() timeline of one CTA of the attention-backward kernel into buf (>= 3*1024 int64, device);
