@@ -307,7 +307,7 @@ int dcv_block_bwd_cls(const dcv_dims* dims, const dcv_block_params* p, const dcv
   return block_bwd_cls(*dims, *p, *a, *g, *ws, dres_c, dres_c_bf16, dres, dres_bf16, dbias_prev, ST(stream));
 }
 
-int dcv_embed_fwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const float* x,
+int dcv_embed_fwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const void* x,
                   const int* idx, const int* gid, const dcv_embed_acts* a, void* stream) {
   if (!dims || !cfg || !p || !a) return set_error(DCV_ERR_INVALID, "dcv_embed_fwd: null struct");
   return embed_fwd(*dims, *cfg, *p, x, idx, gid, *a, ST(stream));

@@ -23,9 +23,13 @@ namespace dcv {
 // One CTA per (b, c', hp) strip of P image rows: reads are full 128-byte lines along W,
 // writes are 8-byte pieces that fill whole 32-byte sectors.
 // ---------------------------------------------------------------------------------
+// U8: x holds raw uint8 pixels and the loader's per-channel standardisation (x - mean[c]) / std[c] (reference
+// datasets/dataset_utils.py:44, jump_cp_transforms.py:119-121) is applied here, on the device: the H2D copy shrinks 4x.
+template <bool U8>
 __global__ void __launch_bounds__(256)
-im2col_gather_kernel(const float* __restrict__ x, const int* __restrict__ idx, __nv_bfloat16* __restrict__ patches,
-                     int C, int Cs, int H, int W, int P) {
+im2col_gather_kernel(const void* __restrict__ xv, const int* __restrict__ idx, __nv_bfloat16* __restrict__ patches,
+                     const float* __restrict__ pix_mean, const float* __restrict__ pix_inv_std, int C, int Cs, int H,
+                     int W, int P) {
   const int hp_count = H / P, wp_count = W / P;
   int strip = blockIdx.x;
   const int hp = strip % hp_count;
@@ -33,13 +37,26 @@ im2col_gather_kernel(const float* __restrict__ x, const int* __restrict__ idx, _
   const int cs = strip % Cs;
   const int b = strip / Cs;
   const int c_src = idx ? __ldg(idx + cs) : cs;
-  const float* src = x + ((static_cast<size_t>(b) * C + c_src) * H + static_cast<size_t>(hp) * P) * W;
+  const size_t src_off = ((static_cast<size_t>(b) * C + c_src) * H + static_cast<size_t>(hp) * P) * W;
+  const float* src = reinterpret_cast<const float*>(xv) + src_off;
+  const uint8_t* src8 = reinterpret_cast<const uint8_t*>(xv) + src_off;
+  float mu = 0.f, is = 1.f;
+  if (U8 && pix_mean != nullptr) {
+    mu = __ldg(pix_mean + c_src);
+    is = __ldg(pix_inv_std + c_src);
+  }
   const int KK = P * P;
   __nv_bfloat16* dst = patches + ((static_cast<size_t>(b) * Cs + cs) * hp_count + hp) * wp_count * (3 * KK);
   const int w4 = W >> 2;
   for (int i = threadIdx.x; i < P * w4; i += blockDim.x) {
     const int ph = i / w4, wq = i - ph * w4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(ph) * W) + wq);
+    float4 v;
+    if (U8) {
+      const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(src8 + static_cast<size_t>(ph) * W) + wq);
+      v = make_float4((u.x - mu) * is, (u.y - mu) * is, (u.z - mu) * is, (u.w - mu) * is);
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(ph) * W) + wq);
+    }
     const int w = wq * 4;
     const int wp = w / P, pw = w - wp * P;
     uint2 hi, lo;
@@ -680,14 +697,20 @@ cls_ln_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ x, 
     default: return set_error(DCV_ERR_UNSUPPORTED, "embed dim %d not instantiated (<=384 or 768)", (D)); \
   }
 
-int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, int Cs, int H, int W, int P,
-                  cudaStream_t st) {
+int im2col_gather(const void* x, int x_is_u8, const float* pix_mean, const float* pix_inv_std, const int* idx,
+                  void* patches, int B, int C, int Cs, int H, int W, int P, cudaStream_t st) {
   if (B <= 0 || Cs <= 0 || C <= 0) return set_error(DCV_ERR_INVALID, "im2col: empty problem");
   if (H % P || W % P || P % 4 || W % 4) return set_error(DCV_ERR_UNSUPPORTED, "im2col: H, W multiples of P; P, W of 4");
   ProfScope prof(PT_IM2COL, st);
   const long long strips = static_cast<long long>(B) * Cs * (H / P);
-  im2col_gather_kernel<<<static_cast<unsigned>(strips), 256, 0, st>>>(x, idx, reinterpret_cast<__nv_bfloat16*>(patches),
-                                                                        C, Cs, H, W, P);
+  if ((pix_mean == nullptr) != (pix_inv_std == nullptr))
+    return set_error(DCV_ERR_INVALID, "im2col: pix_mean and pix_inv_std must be given together");
+  if (x_is_u8)
+    im2col_gather_kernel<true><<<static_cast<unsigned>(strips), 256, 0, st>>>(
+        x, idx, reinterpret_cast<__nv_bfloat16*>(patches), pix_mean, pix_inv_std, C, Cs, H, W, P);
+  else
+    im2col_gather_kernel<false><<<static_cast<unsigned>(strips), 256, 0, st>>>(
+        x, idx, reinterpret_cast<__nv_bfloat16*>(patches), nullptr, nullptr, C, Cs, H, W, P);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -98,8 +98,8 @@ int adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long 
 int sumsq_f32(const float* g, long long n, float* out, cudaStream_t st);
 
 // ---- embed.cu ----
-int im2col_gather(const float* x, const int* idx, void* patches, int B, int C, int Cs, int H, int W, int P,
-                  cudaStream_t st);
+int im2col_gather(const void* x, int x_is_u8, const float* pix_mean, const float* pix_inv_std, const int* idx,
+                  void* patches, int B, int C, int Cs, int H, int W, int P, cudaStream_t st);
 int split_weight(const float* w, void* ws, int D, int K, cudaStream_t st);
 int embed_addend(const float* bias, const float* chan_embed, const int* gid, const float* pos_patch, const float* cls,
                  const float* pos0, float* addend, float* tokens, int B, int Cs, int N, int D, cudaStream_t st);
@@ -132,7 +132,7 @@ int block_fwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_
 int block_bwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, const dcv_block_grads& g,
                   const dcv_block_ws& ws, float* dres_c, void* dres_c_bf16, float* dres, void* dres_bf16,
                   float* dbias_prev, cudaStream_t st);
-int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const float* x,
+int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const void* x,
               const int* idx, const int* gid, const dcv_embed_acts& a, cudaStream_t st);
 int embed_bwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const int* gid,
               const dcv_embed_acts& a, const dcv_embed_grads& g, const dcv_embed_ws& ws, const float* G,

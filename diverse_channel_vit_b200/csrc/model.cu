@@ -117,14 +117,14 @@ static int check_embed(const dcv_embed_dims& d) {
   return 0;
 }
 
-int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const float* x,
+int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed_params& p, const void* x,
               const int* idx, const int* gid, const dcv_embed_acts& a, cudaStream_t st) {
   DCV_TRY(check_embed(d));
   if (!x || !gid || !a.patches || !a.wsplit || !a.addend || !a.tokens || !a.extra)
     return set_error(DCV_ERR_INVALID, "embed_fwd: null pointer");
   const int N = (d.H / d.P) * (d.W / d.P), T = d.Cs * N, K = d.P * d.P, D = d.D;
   // DCS gather + unfold (dichavit.py:210, :377)
-  DCV_TRY(im2col_gather(x, idx, a.patches, d.B, d.C, d.Cs, d.H, d.W, d.P, st));
+  DCV_TRY(im2col_gather(x, cfg.x_is_u8, p.pix_mean, p.pix_inv_std, idx, a.patches, d.B, d.C, d.Cs, d.H, d.W, d.P, st));
   DCV_TRY(split_weight(p.proj_w, a.wsplit, D, K, st));
   // positional embedding of the patches: raw or bicubic-resampled (dichavit.py:529-552)
   const float* pos_patch = p.pos + D;

@@ -71,11 +71,12 @@ class _EmbedDims(Structure):
 
 class _EmbedCfg(Structure):
     _fields_ = [("lambda_tdl", c_float), ("lambda_cdl", c_float), ("gamma_s", c_float), ("gamma_d", c_float),
-                ("cdl_scale", c_float), ("reverse_pos_pairs", c_int), ("use_square", c_int)]
+                ("cdl_scale", c_float), ("reverse_pos_pairs", c_int), ("use_square", c_int), ("x_is_u8", c_int)]
 
 
 class _EmbedParams(Structure):
-    _fields_ = [(n, c_void_p) for n in ("proj_w", "proj_b", "chan_embed", "proxies", "cls", "pos", "pos_map")]
+    _fields_ = [(n, c_void_p) for n in ("proj_w", "proj_b", "chan_embed", "proxies", "cls", "pos", "pos_map", "pix_mean",
+                                        "pix_inv_std")]
 
 
 class _EmbedGrads(Structure):
@@ -429,6 +430,8 @@ class DiChaViT(nn.Module):
         self._pg = None
         self._comm_stream = None
         self.last_losses: Dict[str, torch.Tensor] = {}
+        self._x_is_u8 = False
+        self._pix_norm = None
         self._plan_cache: Dict[tuple, dict] = {}
         self._bp_cache = None
         self.direct_grad = False  # see _DiChaViTFn.backward
@@ -524,7 +527,20 @@ class DiChaViT(nn.Module):
             raise DcvError("DiChaViT (B200-native) needs a CUDA tensor: there is no CPU fallback")
         if x.dim() != 4:
             raise ValueError("x must be [B, C, H, W]")
-        x = x.contiguous().float()
+        # uint8 input: the loader's per-channel standardisation runs inside the patch-gather kernel (8(f) #3);
+        # kwargs pixel_mean / pixel_std: [C] tensors or sequences in the order of x's channels
+        self._x_is_u8 = x.dtype == torch.uint8
+        self._pix_norm = None
+        if self._x_is_u8:
+            x = x.contiguous()
+            if kwargs.get("pixel_mean") is not None:
+                mean = torch.as_tensor(kwargs["pixel_mean"], dtype=torch.float32, device=x.device).contiguous()
+                std = torch.as_tensor(kwargs["pixel_std"], dtype=torch.float32, device=x.device).contiguous()
+                if mean.numel() != x.shape[1] or std.numel() != x.shape[1]:
+                    raise ValueError("pixel_mean / pixel_std must have one entry per input channel")
+                self._pix_norm = (mean, (1.0 / std).contiguous())
+        else:
+            x = x.contiguous().float()
         self._ensure_flat(x.device)
         pe = self.feature_extractor.patch_embed
         cs, idx, gid = pe.select_channels(chunk_name, x.shape[1], x.device)
@@ -607,15 +623,18 @@ class DiChaViT(nn.Module):
         # mode and throws the value away -- here the kernels are simply not launched
         l_tdl = float(cfg.ortho_loss_v1_lambda) if self.training else 0.0
         l_cdl = float(cfg.proxy_loss_lambda) if self.training else 0.0
+        norm = getattr(self, "_pix_norm", None)
         ecfg = _EmbedCfg(l_tdl, l_cdl, float(cfg.gamma_s), float(cfg.gamma_d), float(pe.channel_scale),
-                         int(bool(cfg.reverse_pos_pairs)), int(bool(cfg.use_square)))
+                         int(bool(cfg.reverse_pos_pairs)), int(bool(cfg.use_square)), int(self._x_is_u8))
         has_prox = hasattr(pe, "channel_emb_proxies")
         pos_map = self._pos_map(pl["W"], pl["H"], device) if use_map else None
         ce_ptr = self._ce_override.data_ptr() if getattr(self, "_ce_override", None) is not None else \
             self._fptr(pe.channel_embed.weight)
         ep = _EmbedParams(self._fptr(pe.proj.weight), self._fptr(pe.proj.bias), ce_ptr,
                           self._fptr(pe.channel_emb_proxies) if has_prox else None, self._fptr(fe.cls_token),
-                          self._fptr(fe.pos_embed), pos_map.data_ptr() if pos_map is not None else None)
+                          self._fptr(fe.pos_embed), pos_map.data_ptr() if pos_map is not None else None,
+                          norm[0].data_ptr() if norm is not None else None,
+                          norm[1].data_ptr() if norm is not None else None)
         sp = scal.data_ptr()
         acts = _EmbedActs(base + s["patches"], base + s["wsplit"], base + s["pos_patch"], base + s["addend"], base + s["x0"],
                           base + s["S"], base + s["Q"], base + s["rnorm"], base + s["S_all"], base + s["loss_b"],

@@ -191,6 +191,7 @@ typedef struct dcv_embed_cfg {
   float gamma_s, gamma_d;
   float cdl_scale; /* sqrt(1 / temperature), dichavit.py:60 */
   int reverse_pos_pairs, use_square;
+  int x_is_u8; /* 1: x holds raw uint8 pixels, standardised on the device with pix_mean / pix_inv_std */
 } dcv_embed_cfg;
 
 typedef struct dcv_embed_params {
@@ -201,6 +202,8 @@ typedef struct dcv_embed_params {
   const float* cls;        /* [D]                                                          */
   const float* pos;        /* [1 + N, D] pos_embed                                         */
   const float* pos_map;    /* [N, N] bicubic resample matrix, NULL = use pos[1:] unchanged */
+  const float* pix_mean;   /* [C] per input-channel mean of the loader's standardisation (x_is_u8 only; NULL = none) */
+  const float* pix_inv_std; /* [C] 1 / std                                                                      */
 } dcv_embed_params;
 
 typedef struct dcv_embed_grads { /* fp32, accumulated */
@@ -224,9 +227,10 @@ typedef struct dcv_embed_ws {
   float* dpos_patch; /* fp32 [N, D]      */
 } dcv_embed_ws;
 
-/* x fp32 [B, C, H, W]; idx int32 [C'] positions of the sampled channels inside x (NULL = 0..C'-1);
- * gid int32 [C'] their global channel ids (rows of chan_embed / proxies). */
-int dcv_embed_fwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const float* x,
+/* x fp32 (or uint8 when cfg->x_is_u8: the loader's (x - mean) / std of datasets/dataset_utils.py:44 /
+ * jump_cp_transforms.py:119-121 then runs on the device) [B, C, H, W]; idx int32 [C'] positions of the
+ * sampled channels inside x (NULL = 0..C'-1); gid int32 [C'] their global channel ids (rows of chan_embed / proxies). */
+int dcv_embed_fwd(const dcv_embed_dims* dims, const dcv_embed_cfg* cfg, const dcv_embed_params* p, const void* x,
                   const int* idx, const int* gid, const dcv_embed_acts* a, void* stream);
 
 /* G fp32 [B, L, D]: gradient w.r.t. tokens; d_extra: device scalar, gradient w.r.t. the extra loss. */

@@ -291,3 +291,24 @@ def test_direct_grad_mode_equals_autograd_mode():
     (torch.nn.functional.cross_entropy(out, y.cuda()) + extra * xlam).backward()
     k = "feature_extractor.blocks.3.mlp.fc1.weight"
     assert rel_l2(dict(mb.named_parameters())[k].grad, 2 * ga[k]) < 1e-3
+
+
+def test_uint8_input_with_device_side_standardisation():
+    """raw uint8 pixels + per-channel (x - mean) / std applied inside the patch-gather kernel give
+    the same result as feeding the host-standardised float tensor the reference's loaders produce."""
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["tiny_jumpcp"]
+    weights = O.make_weights(oc, has_head, wseed)
+    m = build_cuda_model(oc, mapper, weights).train()
+    g = torch.Generator().manual_seed(5)
+    xu = torch.randint(0, 256, (B, 8, 32, 32), generator=g, dtype=torch.uint8)
+    mean = torch.linspace(90.0, 140.0, 8)
+    std = torch.linspace(40.0, 70.0, 8)
+    xf = (xu.float() - mean[None, :, None, None]) / std[None, :, None, None]
+    out_f, extra_f = m(xf.cuda(), chunk)
+    out_u, extra_u = m(xu.cuda(), chunk, pixel_mean=mean, pixel_std=std)
+    assert rel_l2(out_u, out_f) < ACT_TOL  # 1-ulp input differences get amplified by 12 bf16 blocks
+    assert abs(extra_u.item() - extra_f.item()) <= 1e-4 * abs(extra_f.item())
+    oo = O.forward(xf, weights, oc, mapper[chunk], training=True, has_head=has_head)
+    assert rel_l2(out_u, oo.out) < ACT_TOL
+    (out_u.sum() + extra_u).backward()  # the wgrad consumes the same standardised patches
+    assert torch.isfinite(m.feature_extractor.patch_embed.proj.weight.grad).all()
