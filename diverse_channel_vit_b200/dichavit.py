@@ -927,6 +927,32 @@ class _DiChaViTFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *grads)
 
 
+class ChannelViTAdapt(DiChaViT):
+    """Sibling baseline of the reference (models/channel_vit_adapt.py:ChannelViTAdapt, factory `channelvit_adapt`,
+    SURVEY 8(f) #4): the same channel-adaptive ViT without CDL / TDL and with uniform hierarchical channel sampling
+    (`random.sample`) instead of DCS; forward returns the logits / features only, in train and eval mode alike."""
+
+    def __init__(self, config, **kwargs):
+        class _View(dict):  # the sibling's config has no DiChaViT-specific keys: supply their neutral values
+            __getattr__ = dict.__getitem__
+
+        cfg = _View(config)
+        cfg.update(proxy_loss_lambda=0, ortho_loss_v1_lambda=0, hcs_sampling="none")
+        for k, v in (("hcs_sampling_temp", 0.1), ("gamma_s", 1.0), ("gamma_d", 0.5), ("reverse_pos_pairs", False),
+                     ("use_square", False), ("dropout_tokens_hcs", "none"), ("block_type", "block"),
+                     ("freeze_channel_emb", False), ("orthogonal_channel_emb_init", False), ("learnable_temp", False)):
+            cfg.setdefault(k, v)
+        super().__init__(cfg, **kwargs)
+
+    def forward(self, x, chunk_name, training_chunks=None, init_first_layer=None, new_channel_init=None, **kwargs):
+        out = super().forward(x, chunk_name, training_chunks, init_first_layer, new_channel_init, **kwargs)
+        return out[0] if isinstance(out, tuple) else out
+
+
+def channelvit_adapt(cfg, **kwargs) -> ChannelViTAdapt:
+    return ChannelViTAdapt(config=cfg, **kwargs)
+
+
 def dichavit(cfg, **kwargs) -> DiChaViT:
     """Factory registered under the reference's name (models/dichavit.py:864-865, models/__init__.py:9)."""
     return DiChaViT(config=cfg, **kwargs)

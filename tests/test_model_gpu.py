@@ -312,3 +312,45 @@ def test_uint8_input_with_device_side_standardisation():
     assert rel_l2(out_u, oo.out) < ACT_TOL
     (out_u.sum() + extra_u).backward()  # the wgrad consumes the same standardised patches
     assert torch.isfinite(m.feature_extractor.patch_embed.proj.weight.grad).all()
+
+
+def test_sibling_channelvit_adapt_and_other_sampling_modes():
+    """ChannelViTAdapt (no CDL/TDL, uniform `random.sample` channel sampling, bare-tensor output) and
+    the deterministic DCS variants lowest_cosine / highest_cosine, against the oracle with the same RNG state."""
+    from diverse_channel_vit_b200.dichavit import channelvit_adapt, dichavit
+
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["tiny_jumpcp"]
+    weights = O.make_weights(oc, has_head, wseed)
+    x, y = make_inputs(oc, B, 8, oc.num_classes, iseed)
+    cfg = ref_cfg(oc)
+    cfg["enable_sample"] = True
+    sib = channelvit_adapt(cfg, mapper=mapper)
+    sd = {k: v for k, v in weights.items() if k in sib.state_dict()}
+    assert "feature_extractor.patch_embed.channel_emb_proxies" not in sib.state_dict()
+    sib.load_state_dict(sd)
+    sib = sib.cuda().train()
+    ocs = O.OracleConfig(**{**oc.__dict__, "proxy_loss_lambda": 0.0, "ortho_loss_v1_lambda": 0.0, "enable_sample": True,
+                            "hcs_sampling": "none"})
+    for seed in (0, 1, 2):
+        random.seed(seed)
+        out = sib(x.cuda(), chunk)
+        assert isinstance(out, torch.Tensor)
+        random.seed(seed)
+        _, _, idx = O.dcs_select(weights["feature_extractor.patch_embed.channel_embed.weight"], 0.1, "none")
+        oo = O.forward(x, weights, ocs, mapper[chunk], training=True, has_head=has_head, indices=idx)
+        assert rel_l2(out, oo.out) < ACT_TOL
+        torch.nn.functional.cross_entropy(out, y.cuda()).backward()
+    for mode in ("lowest_cosine", "highest_cosine"):
+        cfg2 = ref_cfg(oc)
+        cfg2["enable_sample"] = True
+        cfg2["hcs_sampling"] = mode
+        m = dichavit(cfg2, mapper=mapper)
+        m.load_state_dict({k: weights[k] for k in m.state_dict()})
+        m = m.cuda().train()
+        pe = m.feature_extractor.patch_embed
+        for seed in range(6):
+            random.seed(seed)
+            c_new, idx, gid = pe.select_channels(chunk, 8, torch.device("cuda"))
+            random.seed(seed)
+            want = O.dcs_select(pe.channel_embed.weight.detach(), 0.1, mode)
+            assert (c_new, idx.tolist()) == (want[0], want[2]), (mode, seed)
