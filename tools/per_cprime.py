@@ -15,10 +15,10 @@ m.direct_grad = True
 pe = m.feature_extractor.patch_embed
 x = torch.randn(32, 8, 224, 224, device="cuda"); y = torch.randint(0, 161, (32,), device="cuda")
 chan = pe.chunk_channels("train", x.device)
-lib = _lib.lib(); nt = lib.dcv_profile_num_tags()
+lib = _lib.lib(); nt = lib.dcv_profile_num_tags(); lib.dcv_profile_tag_name.restype = ctypes.c_char_p
 def step():
     opt.zero_grad(); out, extra = m(x, "train"); (F.cross_entropy(out, y) + extra).backward(); opt.step()
-for cs in (8, 1, 2, 3, 4, 6, 8):
+for cs in (8, 1, 2, 4):
     it = torch.arange(cs, dtype=torch.int32, device="cuda")
     pe.select_channels = lambda *_a, **_k: (cs, it, chan[it.long()].to(torch.int32))
     for _ in range(3): step()
@@ -32,4 +32,7 @@ for cs in (8, 1, 2, 3, 4, 6, 8):
     lib.dcv_profile_start()
     for _ in range(5): step()
     lib.dcv_profile_stop(msb, cnt, nt)
+    names = [lib.dcv_profile_tag_name(i) for i in range(nt)]
+    if cs <= 2:
+        print("   ", {(n.decode() if isinstance(n, bytes) else n): round(msb[i] / 5, 3) for i, n in enumerate(names) if cnt[i]})
     print(f"C'={cs}: step {ms:6.2f} ms (host enqueue {t_host:5.2f} ms), kernel sum {sum(msb)/5:6.2f} ms, img/s {32/ms*1e3:7.0f}", flush=True)
