@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
+    *os.environ.get("DCV_NVCC_EXTRA", "").split(),  # e.g. -DDCV_ATTN_TIMELINE for tools/attn_timeline.py
 ]
 
 

@@ -2,19 +2,22 @@
 // reference models/vit.py:126-141 (softmax(q k^T * scale) v).
 //
 //   prep   : delta[b,h,q] = sum_d dO[q,d] * O[q,d] (0 on the pad rows), dq accumulator cleared
-//   main   : one CTA per (128-key tile, head, image), 1 CTA / SM, looping over 128-query tiles:
-//              S^T  = K Q^T            dP^T = V dO^T                    (SS MMAs, operands K-major)
-//              P^T  = exp2(S^T*sl2 - lse2[q])          -> bf16 into TMEM (A operand of the dV MMA)
-//              dS^T = P^T o (dP^T - delta[q])          -> bf16 into smem (hand-swizzled UMMA tile)
-//              dV  += P^T dO   (TS MMA)     dK += dS^T Q   (SS)      dQ_i = dS K   (SS, A MN-major)
-//            dQ_i is drained TMEM -> swizzled smem -> one cp.reduce.async.bulk.tensor (fp32 add) per
-//            64x... half tile into the [B,H,L,64] accumulator; the softmax scale is folded into the
-//            dK epilogue and the finish kernel.
+//   main   : one CTA per (128-key tile, head, image), 1 CTA / SM, looping over 128-query tiles i:
+//              S_i^T  = K Q_i^T          dP_i^T = V dO_i^T                  (SS MMAs, operands K-major)
+//              P_i^T  = exp2(S_i^T*sl2 - lse2[q])      -> bf16 into TMEM (A operand of the dV MMA)
+//              dS_i^T = P_i^T o (dP_i^T - delta[q])    -> bf16 into smem (hand-swizzled UMMA tile)
+//              dV  += P_i^T dO_i (TS MMA)   dK += dS_i^T Q_i (SS)   dQ_i = dS_i K   (SS, A MN-major)
+//            Software pipeline: in phase i the compute threads produce P_i (MUFU-bound) and dS_{i-1} (FMA pipe)
+//            in the same instruction stream; S_{i+1} / dP_i are issued while phase i is still running (as soon as
+//            their TMEM inputs sit in registers), dK_{i-1} / dV_i / dQ_{i-1} right after it.
+//            dQ_i is drained TMEM -> swizzled smem -> cp.reduce.async.bulk.tensor (fp32 add) into the [B,H,L,64]
+//            accumulator; the softmax scale is folded into the dK epilogue and the finish kernel.
 //   finish : scale * dq_acc fp32 [B,H,L,64] -> bf16 dqkv[:, :, 0:D]
 //
-// Warp roles (320 threads): warps 0-7 = two compute warpgroups, warpgroup g owns the query columns
-// [64g, 64g+64) of every S^T / dP^T tile (TMEM lane = key row = 32*(warp%4)+lane) and the dQ columns
-// [32g, 32g+32); warp 8 = TMA producer; warp 9 = MMA issuer + TMEM owner.
+// Warp roles (512 threads, registers re-balanced with setmaxnreg): warps 0-7 = two compute warpgroups, warpgroup g
+// owns the query columns [64g, 64g+64) of every S^T / dP^T tile (TMEM lane = key row = 32*(warp%4)+lane);
+// warp 8 = TMA producer; warp 9 = front MMA issuer (S, dP; owns TMEM); warp 10 = back MMA issuer (dK, dV, dQ);
+// warps 12-15 drain dQ.
 // TMEM columns: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,448) | P^T bf16 [448,512)
 #include "common.cuh"
 #include "host.h"
@@ -36,10 +39,14 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // debug timeline: when non-null, CTA (1,0,0) records clock64() stamps: slot = role * 1024 + iter * 8 + point
 __device__ long long* g_attn_timeline = nullptr;
+#ifdef DCV_ATTN_TIMELINE
 #define TL(role, it, pt)                                                                      \
   do {                                                                                        \
     if (tl) tl[(role) * 1024 + (it) * 8 + (pt)] = clock64();                                   \
   } while (0)
+#else
+#define TL(role, it, pt) ((void)tl)
+#endif
 
 struct AttnBwdParams {
   int B, L, H, D, Lp;
@@ -51,21 +58,124 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv; // [B,L,3D]
 };
 
-// smem: K,V | Q,dO x2 stages | dS^T (2 chunks of [128 kv][64 q]) | dQ staging (2 boxes of [128 q][32] fp32)
-//       | lse2 / delta of the query tile x2 stages (TMA bulk copies riding on the Q/dO barrier)
+// smem: K,V | Q x3 stages | dO x2 stages | dS^T x2 buffers (each 2 chunks of [128 kv][64 q]) |
+//       dQ staging (2 boxes of [128 q][32] fp32) | lse2 / delta of the query tile x3 stages (TMA bulk copies riding
+//       on the Q barrier)
+constexpr int kQStages = 3;
 constexpr int kStatBytes = 2 * kTq * 4;  // 128 lse2 + 128 delta
-constexpr int kBwdSmem = 2 * kTile16K + 4 * kTile16K + 2 * kTile16K + 2 * kTile16K + 2 * kStatBytes + 1024 + 256;
-constexpr int kBwdThreads = 448;  // 8 compute warps + TMA warp + MMA warp + 4 dQ-drain warps
-
-__device__ __forceinline__ void wg_barrier(int g) {  // named barrier 1 + g, the 128 threads of warpgroup g
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-}
+constexpr int kBwdSmem = 2 * kTile16K + kQStages * kTile16K + 2 * kTile16K + 4 * kTile16K + 2 * kTile16K +
+                         kQStages * kStatBytes + 1024 + 256;
+// warpgroups 0-3: compute | warpgroup 4: TMA warp, two MMA-issuer warps, 1 idle | warpgroup 5: dQ drain
+constexpr int kBwdThreads = 768;
+constexpr int kWarpTma = 16, kWarpFront = 17, kWarpBack = 18, kWarpDrain0 = 20;
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                :
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+
+struct BwdBars {
+  uint64_t kv_full, q_full[kQStages], q_empty[kQStages], do_full[2], do_empty[2];
+  uint64_t s_full, dp_full, s_consumed, dp_consumed, phase_done, p_free, ds_free[2];
+  uint64_t dq_full, dq_empty, dkv_full;
+  uint32_t tmem_slot;
+};
+
+// One software-pipelined phase of a compute thread (key row r, query columns [32cg, 32cg+32) of the tile):
+//   A part (tile i)  : P^T = exp2(S^T * sl2 - lse2[q])                   -> bf16 into TMEM at the end of the phase
+//   B part (tile i-1): dS^T = P^T o (dP^T - delta[q]), P^T re-read from TMEM -> bf16 into the swizzled smem tile
+// The B part's FMA-pipe work fills the issue slots the A part leaves while it waits on the MUFU; four compute warps
+// per SM sub-partition hide the dependent-instruction latency.
+template <bool HAS_A, bool HAS_B>
+__device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_base, BwdBars* bars, uint8_t* sStat,
+                                          uint8_t* sdS, uint32_t tS, uint32_t tdP, uint32_t tP, float sl2, bool zero_row,
+                                          long long* tl) {
+  uint32_t s[32];
+  TL(1 + cg, i, 0);
+  if (HAS_A) {
+    mbar_wait(&bars->q_full[i % kQStages], (i / kQStages) & 1);  // lse2 / delta landed (long before S_i)
+    mbar_wait(&bars->s_full, i & 1);
+    tc_fence_after();
+    tmem_ld32(tS + lane_base + cg * 32, s);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(&bars->s_consumed);  // S_{i+1} may overwrite tS
+  }
+  TL(1 + cg, i, 1);
+  uint32_t sdS_g = 0, s_del = 0;
+  if (HAS_B) {
+    const int j = i - 1;
+    mbar_wait(&bars->dp_full, j & 1);
+    if (j >= 2) mbar_wait(&bars->ds_free[j & 1], ((j >> 1) - 1) & 1);  // dK_{j-2}, dQ_{j-2} have read this buffer
+    tc_fence_after();
+    sdS_g = smem_u32(sdS + (j & 1) * (2 * kTile16K) + (cg >> 1) * kTile16K);
+    s_del = smem_u32(sStat + (j % kQStages) * kStatBytes) + kTq * 4 + cg * 128;
+  }
+  TL(1 + cg, i, 2);
+  const uint32_t s_lse = smem_u32(sStat + (i % kQStages) * kStatBytes) + cg * 128;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {  // 16 query columns per step
+    uint32_t d[16], pp[8];
+    if (HAS_B) {
+      tmem_ld16(tdP + lane_base + cg * 32 + 16 * c, d);
+      tmem_ld8(tP + lane_base + cg * 16 + 8 * c, pp);
+    }
+    if (HAS_A) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 l4 = ld_shared_f4(s_lse + (16 * c + 4 * q) * 4);
+        s[16 * c + 4 * q + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 0]), sl2, -l4.x)));
+        s[16 * c + 4 * q + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 1]), sl2, -l4.y)));
+        s[16 * c + 4 * q + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 2]), sl2, -l4.z)));
+        s[16 * c + 4 * q + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 3]), sl2, -l4.w)));
+      }
+    }
+    if (HAS_B) {
+      tmem_ld_wait();
+      if (c == 1) {
+        tc_fence_before();
+        mbar_arrive(&bars->dp_consumed);  // dP_i may overwrite tdP
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {  // 8 queries -> one 16-byte slot of the swizzled dS^T tile
+        const float4 da = ld_shared_f4(s_del + (16 * c + 8 * v) * 4), db = ld_shared_f4(s_del + (16 * c + 8 * v + 4) * 4);
+        const float2 p0 = unpack_bf16(pp[4 * v + 0]), p1 = unpack_bf16(pp[4 * v + 1]);
+        const float2 p2 = unpack_bf16(pp[4 * v + 2]), p3 = unpack_bf16(pp[4 * v + 3]);
+        const float e0 = p0.x * (__uint_as_float(d[8 * v + 0]) - da.x);
+        const float e1 = p0.y * (__uint_as_float(d[8 * v + 1]) - da.y);
+        const float e2 = p1.x * (__uint_as_float(d[8 * v + 2]) - da.z);
+        const float e3 = p1.y * (__uint_as_float(d[8 * v + 3]) - da.w);
+        const float e4 = p2.x * (__uint_as_float(d[8 * v + 4]) - db.x);
+        const float e5 = p2.y * (__uint_as_float(d[8 * v + 5]) - db.y);
+        const float e6 = p3.x * (__uint_as_float(d[8 * v + 6]) - db.z);
+        const float e7 = p3.y * (__uint_as_float(d[8 * v + 7]) - db.w);
+        st_shared_v4(sdS_g + sw128_offset(r, 4 * (cg & 1) + 2 * c + v), pack_bf16(e0, e1), pack_bf16(e2, e3),
+                     pack_bf16(e4, e5), pack_bf16(e6, e7));
+      }
+    }
+  }
+  TL(1 + cg, i, 3);
+  if (HAS_A) {
+    if (i > 0) {  // dV_{i-1} has finished reading P_{i-1}
+      mbar_wait(&bars->p_free, (i - 1) & 1);
+      tc_fence_after();
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      pk[j] = zero_row ? 0u : pack_bf16(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1]));
+    tmem_st16(tP + lane_base + cg * 16, pk);
+    tmem_st_wait();
+  }
+  if (HAS_B) fence_proxy_async_smem();
+  // last phase: the back issuer must have consumed phase_done(i-1) before this phase completes the barrier again
+  // (mbarrier waits only tell the current phase from the previous one)
+  if (!HAS_A) mbar_wait(&bars->p_free, (i - 1) & 1);
+  tc_fence_before();
+  mbar_arrive(&bars->phase_done);
+  TL(1 + cg, i, 4);
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -75,23 +185,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + kTile16K;
-  uint8_t* sQ = sV + kTile16K;        // 2 stages
-  uint8_t* sdO = sQ + 2 * kTile16K;   // 2 stages
-  uint8_t* sdS = sdO + 2 * kTile16K;  // [2 q-chunks][128 kv rows][128 B] swizzled
-  uint8_t* sdQ = sdS + 2 * kTile16K;  // [2 d-halves][128 q rows][32 fp32] swizzled
-  uint8_t* sStat = sdQ + 2 * kTile16K;  // [2 stages][lse2 128 | delta 128] fp32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * kStatBytes);
-  uint64_t* kv_full = bars;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* dp_full = bars + 6;
-  uint64_t* p_ready = bars + 7;
-  uint64_t* ds_ready = bars + 8;
-  uint64_t* dq_full = bars + 9;
-  uint64_t* dq_empty = bars + 10;
-  uint64_t* dkv_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* sQ = sV + kTile16K;               // 3 stages
+  uint8_t* sdO = sQ + kQStages * kTile16K;   // 2 stages
+  uint8_t* sdS = sdO + 2 * kTile16K;         // [2 buffers][2 q-chunks][128 kv rows][128 B] swizzled
+  uint8_t* sdQ = sdS + 4 * kTile16K;         // [2 d-halves][128 q rows][32 fp32] swizzled
+  uint8_t* sStat = sdQ + 2 * kTile16K;       // [3 stages][lse2 128 | delta 128] fp32
+  BwdBars* bars = reinterpret_cast<BwdBars*>(sStat + kQStages * kStatBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,176 +199,198 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   const int b = blockIdx.z;
   const int n_q = p.n_q;
   long long* tl = (g_attn_timeline && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
-                   (warp == 9 || warp == 0 || warp == 4))
+                   (warp == kWarpFront || warp == kWarpBack || warp == 0 || warp == 4))
                       ? g_attn_timeline
                       : nullptr;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
     tma_prefetch_desc(&map_dq);
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&qdo_full[i], 1);
-      mbar_init(&qdo_empty[i], 1);
+    mbar_init(&bars->kv_full, 1);
+    for (int i = 0; i < kQStages; ++i) {
+      mbar_init(&bars->q_full[i], 1);
+      mbar_init(&bars->q_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(dp_full, 1);
-    mbar_init(p_ready, 256);
-    mbar_init(ds_ready, 256);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128);  // the four drain warps
-    mbar_init(dkv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->do_full[i], 1);
+      mbar_init(&bars->do_empty[i], 2);  // dP_i (front issuer) and dV_i (back issuer) have both read dO_i
+      mbar_init(&bars->ds_free[i], 1);
+    }
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->dp_full, 1);
+    mbar_init(&bars->s_consumed, 512);
+    mbar_init(&bars->dp_consumed, 512);
+    mbar_init(&bars->phase_done, 512);
+    mbar_init(&bars->p_free, 1);
+    mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dq_empty, 128);  // the four drain warps
+    mbar_init(&bars->dkv_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == kWarpFront) tmem_alloc(&bars->tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384, tP = tmem_base + 448;
 
-  if (warp == 8) {
-    // ------------------------------------ TMA producer ------------------------------------
-    if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * kTile16K);
-      tma_load_3d(sK, &map_qkv, kv_full, p.D + h * kHd, kv0, b);
-      tma_load_3d(sV, &map_qkv, kv_full, 2 * p.D + h * kHd, kv0, b);
-      for (int i = 0; i < n_q; ++i) {
-        const int st = i & 1;
-        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&qdo_full[st], 2 * kTile16K + kStatBytes);
-        tma_load_3d(sQ + st * kTile16K, &map_qkv, &qdo_full[st], h * kHd, i * kTq, b);
-        tma_load_3d(sdO + st * kTile16K, &map_do, &qdo_full[st], h * kHd, i * kTq, b);
-        const size_t so = (static_cast<size_t>(b) * p.H + h) * p.Lp + static_cast<size_t>(i) * kTq;
-        bulk_load_1d(sStat + st * kStatBytes, p.lse2 + so, kTq * 4, &qdo_full[st]);
-        bulk_load_1d(sStat + st * kStatBytes + kTq * 4, p.delta + so, kTq * 4, &qdo_full[st]);
+  if (warp >= kWarpTma && warp < kWarpDrain0) {
+    setmaxnreg_dec<40>();
+    if (warp == kWarpTma) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars->kv_full, 2 * kTile16K);
+        tma_load_3d(sK, &map_qkv, &bars->kv_full, p.D + h * kHd, kv0, b);
+        tma_load_3d(sV, &map_qkv, &bars->kv_full, 2 * p.D + h * kHd, kv0, b);
+        for (int i = 0; i < n_q; ++i) {
+          const int sq = i % kQStages, sd = i & 1;
+          if (i >= kQStages) mbar_wait(&bars->q_empty[sq], ((i / kQStages) - 1) & 1);
+          mbar_arrive_expect_tx(&bars->q_full[sq], kTile16K + kStatBytes);
+          tma_load_3d(sQ + sq * kTile16K, &map_qkv, &bars->q_full[sq], h * kHd, i * kTq, b);
+          const size_t so = (static_cast<size_t>(b) * p.H + h) * p.Lp + static_cast<size_t>(i) * kTq;
+          bulk_load_1d(sStat + sq * kStatBytes, p.lse2 + so, kTq * 4, &bars->q_full[sq]);
+          bulk_load_1d(sStat + sq * kStatBytes + kTq * 4, p.delta + so, kTq * 4, &bars->q_full[sq]);
+          if (i >= 2) mbar_wait(&bars->do_empty[sd], ((i >> 1) - 1) & 1);
+          mbar_arrive_expect_tx(&bars->do_full[sd], kTile16K);
+          tma_load_3d(sdO + sd * kTile16K, &map_do, &bars->do_full[sd], h * kHd, i * kTq, b);
+        }
       }
-    }
-  } else if (warp == 9) {
-    // ------------------------------------- MMA issuer -------------------------------------
-    // The whole warp walks the loop (all lanes wait on the barriers) and ONE elected lane issues the MMAs /
-    // commits inside warp-uniform control flow: under `if (lane == 0)` the compiler has to assume divergent
-    // operands and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop, which made the
-    // single issuing thread -- not the tensor pipe -- the bottleneck of this kernel.
-    {
+    } else if (warp == kWarpFront) {
+      // ---------------------------------- front MMA issuer ----------------------------------
+      // S_{i+1} as soon as S_i sits in the compute threads' registers, dP_i as soon as dP_{i-1} has been read.
+      // The whole warp walks the loop (all lanes wait on the barriers) and ONE elected lane issues the MMAs /
+      // commits inside warp-uniform control flow: under `if (lane == 0)` the compiler has to assume divergent
+      // operands and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop.
+      // A single warp runs its dependent instruction stream at ~5 clk per instruction, so the issue work of one
+      // (q-tile, k-tile) pair is split over two warps (this one and the back issuer, warp 10).
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
-      constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);   // dV, dK : A (TMEM) K-major, B MN-major
-      constexpr uint32_t id_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ     : A MN-major, B MN-major
       const uint64_t dK_k = make_desc_kmajor(smem_u32(sK));
       const uint64_t dV_k = make_desc_kmajor(smem_u32(sV));
-      const uint64_t dK_mn = make_desc_mnmajor(smem_u32(sK), kTile16K);
-      const uint64_t dS_mn = make_desc_mnmajor(smem_u32(sdS), kTile16K);
-      const uint64_t dS_k0 = make_desc_kmajor(smem_u32(sdS));
-      const uint64_t dS_k1 = make_desc_kmajor(smem_u32(sdS + kTile16K));
-
-      mbar_wait(kv_full, 0);
-      mbar_wait(&qdo_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t dQ_k = make_desc_kmajor(smem_u32(sQ));
-        const uint64_t dO_k = make_desc_kmajor(smem_u32(sdO));
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, dK_k + 2 * k, dQ_k + 2 * k, id_s, k ? 1u : 0u);
-          umma_commit(s_full);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dO_k + 2 * k, id_s, k ? 1u : 0u);
-          umma_commit(dp_full);
-        }
-        __syncwarp();
-      }
-      for (int i = 0; i < n_q; ++i) {
-        const int st = i & 1;
-        const uint64_t dQ_mn = make_desc_mnmajor(smem_u32(sQ + st * kTile16K), kTile16K);
-        const uint64_t dO_mn = make_desc_mnmajor(smem_u32(sdO + st * kTile16K), kTile16K);
-        const uint32_t acc = i ? 1u : 0u;
-        // dV += P^T dO_i  (A = P^T from TMEM: 16 q per K step = 8 packed columns)
-        TL(0, i, 0);
-        mbar_wait(p_ready, i & 1);
-        tc_fence_after();
-        TL(0, i, 1);
-        if (elect_one()) {
-          umma_ts(tdV, tP, dO_mn, id_kv, acc);
-#pragma unroll
-          for (int k = 1; k < 8; ++k) umma_ts(tdV, tP + 8 * k, dO_mn + 128 * k, id_kv, 1u);
-        }
-        __syncwarp();
-        // S^T of the next query tile may overwrite tS now (phase A of tile i has consumed it)
-        uint64_t dOn_k = 0;
+      const uint64_t dQ_k0 = make_desc_kmajor(smem_u32(sQ));     // + stage * (16 KB >> 4)
+      const uint64_t dO_k0 = make_desc_kmajor(smem_u32(sdO));
+      mbar_wait(&bars->kv_full, 0);
+      for (int i = -1; i < n_q; ++i) {
         if (i + 1 < n_q) {
-          const int st1 = (i + 1) & 1;
-          mbar_wait(&qdo_full[st1], ((i + 1) >> 1) & 1);
+          const int s1 = (i + 1) % kQStages;
+          if (i >= 0) mbar_wait(&bars->s_consumed, i & 1);
+          mbar_wait(&bars->q_full[s1], ((i + 1) / kQStages) & 1);
           tc_fence_after();
-          const uint64_t dQn_k = make_desc_kmajor(smem_u32(sQ + st1 * kTile16K));
-          dOn_k = make_desc_kmajor(smem_u32(sdO + st1 * kTile16K));
+          const uint64_t dQn_k = dQ_k0 + static_cast<uint64_t>(s1 * (kTile16K >> 4));
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_ss(tS, dK_k + 2 * k, dQn_k + 2 * k, id_s, k ? 1u : 0u);
-            umma_commit(s_full);
+            umma_commit(&bars->s_full);
           }
           __syncwarp();
         }
-        // dK += dS^T Q_i ; dQ_i = dS K
-        TL(0, i, 2);
-        mbar_wait(ds_ready, i & 1);
-        tc_fence_after();
-        TL(0, i, 3);
-        if (elect_one()) {
-          umma_ss(tdK, dS_k0, dQ_mn, id_kv, acc);
-#pragma unroll
-          for (int k = 1; k < 8; ++k)
-            umma_ss(tdK, (k < 4 ? dS_k0 : dS_k1) + 2 * (k & 3), dQ_mn + 128 * k, id_kv, 1u);
-        }
-        __syncwarp();
-        if (i > 0) {  // the compute warpgroups have drained dQ_{i-1} out of TMEM
-          mbar_wait(dq_empty, (i - 1) & 1);
+        TL(0, i + 1, 0);
+        if (i >= 0) {
+          if (i > 0) mbar_wait(&bars->dp_consumed, (i - 1) & 1);
+          mbar_wait(&bars->do_full[i & 1], (i >> 1) & 1);
           tc_fence_after();
-        }
-        TL(0, i, 4);
-        if (elect_one()) {
+          const uint64_t dO_k = dO_k0 + static_cast<uint64_t>((i & 1) * (kTile16K >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_ss(tdQ, dS_mn + 128 * k, dK_mn + 128 * k, id_dq, k ? 1u : 0u);
-          umma_commit(dq_full);
-          umma_commit(&qdo_empty[st]);
-          if (i + 1 < n_q) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dOn_k + 2 * k, id_s, k ? 1u : 0u);
-            umma_commit(dp_full);
+            for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dO_k + 2 * k, id_s, k ? 1u : 0u);
+            umma_commit(&bars->dp_full);
+            umma_commit(&bars->do_empty[i & 1]);
           }
+          __syncwarp();
         }
-        __syncwarp();
-        TL(0, i, 5);
+        TL(0, i + 1, 1);
       }
-      if (elect_one()) umma_commit(dkv_full);
+    } else if (warp == kWarpBack) {
+      // ----------------------------------- back MMA issuer -----------------------------------
+      // After phase i (P_i in TMEM, dS_{i-1} in smem): dK_{i-1} (frees the Q stage), dV_i (frees P and the dO
+      // stage), dQ_{i-1}.
+      constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);   // dV, dK : A K-major, B MN-major
+      constexpr uint32_t id_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ     : A MN-major, B MN-major
+      const uint64_t dK_mn = make_desc_mnmajor(smem_u32(sK), kTile16K);
+      const uint64_t dQ_mn0 = make_desc_mnmajor(smem_u32(sQ), kTile16K);
+      const uint64_t dO_mn0 = make_desc_mnmajor(smem_u32(sdO), kTile16K);
+      const uint64_t dS_k00 = make_desc_kmajor(smem_u32(sdS));
+      const uint64_t dS_mn0 = make_desc_mnmajor(smem_u32(sdS), kTile16K);
+      mbar_wait(&bars->kv_full, 0);
+      for (int i = 0; i <= n_q; ++i) {
+        const int j = i - 1;  // tile whose dS^T was produced in phase i
+        mbar_wait(&bars->phase_done, i & 1);
+        tc_fence_after();
+        TL(3, i, 0);
+        if (i > 0) {  // dK += dS_j^T Q_j
+          const uint64_t dS_k0 = dS_k00 + static_cast<uint64_t>((j & 1) * (2 * kTile16K >> 4));
+          const uint64_t dS_k1 = dS_k0 + (kTile16K >> 4);
+          const uint64_t dQ_mn = dQ_mn0 + static_cast<uint64_t>((j % kQStages) * (kTile16K >> 4));
+          if (elect_one()) {
+            umma_ss(tdK, dS_k0, dQ_mn, id_kv, j ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+              umma_ss(tdK, (k < 4 ? dS_k0 : dS_k1) + 2 * (k & 3), dQ_mn + 128 * k, id_kv, 1u);
+            umma_commit(&bars->q_empty[j % kQStages]);
+          }
+          __syncwarp();
+        }
+        if (i < n_q) {  // dV += P_i^T dO_i  (A = P^T from TMEM: 16 q per K step = 8 packed columns)
+          const uint64_t dO_mn = dO_mn0 + static_cast<uint64_t>((i & 1) * (kTile16K >> 4));
+          if (elect_one()) {
+            umma_ts(tdV, tP, dO_mn, id_kv, i ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) umma_ts(tdV, tP + 8 * k, dO_mn + 128 * k, id_kv, 1u);
+            umma_commit(&bars->p_free);
+            umma_commit(&bars->do_empty[i & 1]);
+          }
+          __syncwarp();
+        }
+        TL(3, i, 1);
+        if (i > 0) {  // dQ_j = dS_j K
+          if (j > 0) {  // the drain warps have read dQ_{j-1} out of TMEM
+            mbar_wait(&bars->dq_empty, (j - 1) & 1);
+            tc_fence_after();
+          }
+          const uint64_t dS_mn = dS_mn0 + static_cast<uint64_t>((j & 1) * (2 * kTile16K >> 4));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_ss(tdQ, dS_mn + 128 * k, dK_mn + 128 * k, id_dq, k ? 1u : 0u);
+            umma_commit(&bars->dq_full);
+            umma_commit(&bars->ds_free[j & 1]);
+          }
+          __syncwarp();
+        }
+        TL(3, i, 2);
+      }
+      if (elect_one()) umma_commit(&bars->dkv_full);
       __syncwarp();
     }
-  } else if (warp >= 10) {
+  } else if (warp >= kWarpDrain0) {
+    setmaxnreg_dec<56>();
     // ------------------------------------ dQ drain warps ------------------------------------
     // dQ_i (128 queries x 64) : TMEM -> two swizzled [128][32] fp32 boxes in smem -> TMA reduce-add into the
     // [B,H,L,64] accumulator.  Off the critical path of the compute warpgroups.
-    const int q4 = warp & 3;  // TMEM lane quadrant (warps 10..13 -> quadrants 2,3,0,1)
+    const int q4 = warp & 3;  // TMEM lane quadrant
     const int r = q4 * 32 + lane;
-    const int tid_d = threadIdx.x - 320;
+    const int tid_d = threadIdx.x - kWarpDrain0 * 32;
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     const uint32_t sdQ0 = smem_u32(sdQ), sdQ1 = smem_u32(sdQ + kTile16K);
     for (int i = 0; i < n_q; ++i) {
-      mbar_wait(dq_full, i & 1);
+      mbar_wait(&bars->dq_full, i & 1);
       tc_fence_after();
-      uint32_t q0r[32], q1r[32];
-      tmem_ld32(tdQ + lane_base, q0r);
-      tmem_ld32(tdQ + lane_base + 32, q1r);
+      // two 32-column halves, one after the other (keeps this warpgroup at 56 registers).  Vectorised
+      // red.global.add.v4.f32 straight from registers would skip the staging traffic in shared memory (this kernel is
+      // bound by shared-memory bandwidth) but was measured 25 % slower end to end (16-byte L2 reductions).
+      uint32_t qr[32];
+      tmem_ld32(tdQ + lane_base, qr);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_empty);
       if (tid_d == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous reduce has read the boxes
       asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        st_shared_v4(sdQ0 + sw128_offset(r, v), q0r[4 * v], q0r[4 * v + 1], q0r[4 * v + 2], q0r[4 * v + 3]);
-        st_shared_v4(sdQ1 + sw128_offset(r, v), q1r[4 * v], q1r[4 * v + 1], q1r[4 * v + 2], q1r[4 * v + 3]);
-      }
+      for (int v = 0; v < 8; ++v) st_shared_v4(sdQ0 + sw128_offset(r, v), qr[4 * v], qr[4 * v + 1], qr[4 * v + 2], qr[4 * v + 3]);
+      tmem_ld32(tdQ + lane_base + 32, qr);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->dq_empty);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) st_shared_v4(sdQ1 + sw128_offset(r, v), qr[4 * v], qr[4 * v + 1], qr[4 * v + 2], qr[4 * v + 3]);
       fence_proxy_async_smem();
       asm volatile("bar.sync 3, 128;" ::: "memory");
       if (tid_d == 0) {
@@ -280,111 +401,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
     if (tid_d == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reduces fully performed
   } else {
+    setmaxnreg_inc<96>();
     // --------------------------------- compute warpgroups ---------------------------------
-    const int g = warp >> 2;                  // column half
+    const int cg = warp >> 2;                 // 32-column group of the query tile
     const int q4 = warp & 3;                  // TMEM lane quadrant
-    const int r = q4 * 32 + lane;             // key row (phases A/B) or query row (dQ drain)
-    const int tid_g = threadIdx.x & 127;
+    const int r = q4 * 32 + lane;             // key row
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     const bool kv_ok = kv0 + r < p.L;
-    const bool kv_tail = kv0 + kTk > p.L;     // uniform: only the last key tile has masked rows
-    const uint32_t sdS_g = smem_u32(sdS + g * kTile16K);
-    const uint32_t sdQ_g = smem_u32(sdQ + g * kTile16K);
 
-    for (int i = 0; i < n_q; ++i) {
-      // lse2 / delta of this warpgroup's 64 queries (smem, broadcast reads)
-      const uint32_t s_lse = smem_u32(sStat + (i & 1) * kStatBytes) + g * 256;
-      const uint32_t s_del = s_lse + kTq * 4;
-      float pf[64];  // P^T row (64 queries) in fp32, kept for phase B
+    bwd_phase<true, false>(0, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, tl);
+    for (int i = 1; i < n_q; ++i) bwd_phase<true, true>(i, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, tl);
+    bwd_phase<false, true>(n_q, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, tl);
 
-      // ---- phase A: P^T = exp2(S^T * sl2 - lse2[q]) ----
-      TL(1 + g, i, 0);
-      mbar_wait(&qdo_full[i & 1], (i >> 1) & 1);  // stats landed (completes long before S_i)
-      mbar_wait(s_full, i & 1);
-      tc_fence_after();
-      TL(1 + g, i, 1);
-      {
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tS + lane_base + g * 64, s0);
-        tmem_ld32(tS + lane_base + g * 64 + 32, s1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 la = ld_shared_f4(s_lse + j * 16), lb = ld_shared_f4(s_lse + 128 + j * 16);
-          pf[4 * j + 0] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 0]), p.sl2, -la.x));
-          pf[4 * j + 1] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 1]), p.sl2, -la.y));
-          pf[4 * j + 2] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 2]), p.sl2, -la.z));
-          pf[4 * j + 3] = fast_exp2(fmaf(__uint_as_float(s0[4 * j + 3]), p.sl2, -la.w));
-          pf[32 + 4 * j + 0] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 0]), p.sl2, -lb.x));
-          pf[32 + 4 * j + 1] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 1]), p.sl2, -lb.y));
-          pf[32 + 4 * j + 2] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 2]), p.sl2, -lb.z));
-          pf[32 + 4 * j + 3] = fast_exp2(fmaf(__uint_as_float(s1[4 * j + 3]), p.sl2, -lb.w));
-        }
-      }
-      if (kv_tail && !kv_ok) {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) pf[j] = 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(pf[c * 32 + 2 * j], pf[c * 32 + 2 * j + 1]);
-        tmem_st16(tP + lane_base + g * 32 + c * 16, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      TL(1 + g, i, 2);
-
-      // ---- phase B: dS^T = P^T o (dP^T - delta[q])   (softmax scale folded into dK / dQ epilogues) ----
-      TL(1 + g, i, 3);
-      mbar_wait(dp_full, i & 1);
-      tc_fence_after();
-      TL(1 + g, i, 4);
-      {
-        uint32_t d0[32], d1[32];
-        tmem_ld32(tdP + lane_base + g * 64, d0);
-        tmem_ld32(tdP + lane_base + g * 64 + 32, d1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {  // 8 queries -> one 16-byte slot of the swizzled dS^T tile
-          const uint32_t* dr = v < 4 ? d0 : d1;
-          const int o = (v & 3) * 8;
-          const float4 da = ld_shared_f4(s_del + v * 32), db = ld_shared_f4(s_del + v * 32 + 16);
-          const float e0 = pf[v * 8 + 0] * (__uint_as_float(dr[o + 0]) - da.x);
-          const float e1 = pf[v * 8 + 1] * (__uint_as_float(dr[o + 1]) - da.y);
-          const float e2 = pf[v * 8 + 2] * (__uint_as_float(dr[o + 2]) - da.z);
-          const float e3 = pf[v * 8 + 3] * (__uint_as_float(dr[o + 3]) - da.w);
-          const float e4 = pf[v * 8 + 4] * (__uint_as_float(dr[o + 4]) - db.x);
-          const float e5 = pf[v * 8 + 5] * (__uint_as_float(dr[o + 5]) - db.y);
-          const float e6 = pf[v * 8 + 6] * (__uint_as_float(dr[o + 6]) - db.z);
-          const float e7 = pf[v * 8 + 7] * (__uint_as_float(dr[o + 7]) - db.w);
-          st_shared_v4(sdS_g + sw128_offset(r, v), pack_bf16(e0, e1), pack_bf16(e2, e3), pack_bf16(e4, e5),
-                       pack_bf16(e6, e7));
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(ds_ready);
-      TL(1 + g, i, 5);
-    }
-    // ---- epilogue: dK (x scale) and dV rows of this key tile; warpgroup g writes d columns [32g, 32g+32) ----
-    mbar_wait(dkv_full, 0);
+    // ---- epilogue: dK (x scale) and dV rows of this key tile; column group cg writes d columns [16cg, 16cg+16) ----
+    mbar_wait(&bars->dkv_full, 0);
     tc_fence_after();
 #pragma unroll
     for (int which = 0; which < 2; ++which) {  // 0: dK -> column block D, 1: dV -> column block 2D
       const uint32_t tsrc = which == 0 ? tdK : tdV;
       const float mul = which == 0 ? p.scale : 1.0f;
-      uint32_t a[32];
-      tmem_ld32(tsrc + lane_base + g * 32, a);
+      uint32_t a[16];
+      tmem_ld16(tsrc + lane_base + cg * 16, a);
       tmem_ld_wait();
       if (kv_ok) {
         __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + kv0 + r) * (3 * p.D) + (which + 1) * p.D +
-                             h * kHd + g * 32;
+                             h * kHd + cg * 16;
         uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 2; ++v) {
           uint4 o;
           o.x = pack_bf16(__uint_as_float(a[8 * v + 0]) * mul, __uint_as_float(a[8 * v + 1]) * mul);
           o.y = pack_bf16(__uint_as_float(a[8 * v + 2]) * mul, __uint_as_float(a[8 * v + 3]) * mul);
@@ -398,7 +442,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kWarpFront) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -119,6 +119,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Experimental wait / arrive flavours (mode bits: 512 = test_wait spin instead of try_wait, 1024 = one lane polls and
+// the warp re-converges on __syncwarp, 2048 = one arrival per warp instead of one per thread).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int mode) {
+  const bool spin = mode & 512;
+  if (!(mode & 1024) || (threadIdx.x & 31) == 0) {
+    if (spin) {
+      uint32_t spins = 0;
+      while (!mbar_test_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+      }
+    } else {
+      mbar_wait(bar, parity);
+    }
+  }
+  if (mode & 1024) __syncwarp();
+}
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int mode) {
+  if (mode & 2048) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+  } else {
+    mbar_arrive(bar);
+  }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -317,6 +355,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       : "memory");
 }
 
+// Warpgroup register re-allocation (all 4 warps of an aligned warpgroup execute it): roles that only issue
+// TMA / MMA give registers back, the compute warpgroups take them.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane
 // (quadrant_base + i), columns [col, col+32).  The warp may only touch the TMEM
 // lane quadrant 32*(warp_id % 4).
@@ -340,6 +389,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(

@@ -9,16 +9,18 @@ qkv = torch.randn(B * L, 3 * D, device="cuda", generator=g).bfloat16()
 do = torch.randn(B * L, D, device="cuda", generator=g).bfloat16()
 o, lse = K.attn_fwd(qkv, B, L, H)
 K.attn_bwd(qkv, o, do, lse, B, L, H)
-buf = torch.zeros(3 * 1024, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4 * 1024, dtype=torch.int64, device="cuda")
 _lib.lib().dcv_debug_attn_timeline(ctypes.c_void_p(buf.data_ptr()))
 K.attn_bwd(qkv, o, do, lse, B, L, H)
 torch.cuda.synchronize()
 _lib.lib().dcv_debug_attn_timeline(None)
-t = buf.cpu().view(3, 128, 8)
+t = buf.cpu().view(4, 128, 8)
 t0 = int(t[0, 0, 0])
-names = {0: ["mma:wait_p", "mma:got_p", "mma:wait_ds", "mma:got_ds", "mma:got_dqE", "mma:end"],
-         1: ["wg0:top", "wg0:got_S", "wg0:p_arr", "wg0:drained", "wg0:got_dP", "wg0:ds_arr"],
-         2: ["wg1:top", "wg1:got_S", "wg1:p_arr", "wg1:drained", "wg1:got_dP", "wg1:ds_arr"]}
-for i in range(13):
-    for role in range(3):
-        print(f"it{i:2d} " + "  ".join(f"{names[role][p]}={int(t[role, i, p]) - t0:7d}" for p in range(6)))
+names = {0: ["front:S_next", "front:dP"],
+         3: ["back:phase", "back:dKdV", "back:dQ"],
+         1: ["wg0:top", "wg0:S_ld", "wg0:got_dP", "wg0:chunks", "wg0:arrive", "wg0:c0exp", "wg0:c0ldw", "wg0:c0dS"],
+         2: ["wg1:top", "wg1:S_ld", "wg1:got_dP", "wg1:chunks", "wg1:arrive", "wg1:c0exp", "wg1:c0ldw", "wg1:c0dS"]}
+t0 = int(t[1, 0, 0])
+for i in range(14):
+    for role in (0, 3, 1, 2):
+        print(f"it{i:2d} " + "  ".join(f"{names[role][p]}={int(t[role, i, p]) - t0:7d}" for p in range(len(names[role]))))
