@@ -31,6 +31,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// debug timeline (-DDCV_ATTN_TIMELINE): CTA (1,0,0) records clock64() stamps: slot = role * 1024 + iter * 8 + point
+__device__ long long* g_fwd_timeline = nullptr;
+#ifdef DCV_ATTN_TIMELINE
+#define TLF(role, it, pt)                                                  \
+  do {                                                                     \
+    if (tl) tl[(role) * 1024 + (it) * 8 + (pt)] = clock64();                \
+  } while (0)
+#else
+#define TLF(role, it, pt) ((void)tl)
+#endif
+int debug_fwd_timeline(long long* buf) {
+  DCV_CUDA(cudaMemcpyToSymbol(g_fwd_timeline, &buf, sizeof(buf)));
+  return 0;
+}
+
 struct AttnFwdParams {
   int B, L, H, D;
   int Lp;     // row stride of lse2 (L rounded up to 128)
@@ -42,6 +57,11 @@ struct AttnFwdParams {
 constexpr int kFwdStages = 2;
 constexpr int kFwdSmem = kTq * kHd * 2 + kFwdStages * 2 * kTk * kHd * 2 + 1024 + 128;
 
+// Pipeline inside one CTA (a second CTA on the same SM fills the MUFU while this one waits):
+//   softmax j : read S_j into registers -> [s_consumed] -> row max -> exponentials in place -> P_j to TMEM -> [p_full]
+//   MMA warp  : S_{j+1} = Q K_{j+1}^T is issued at s_consumed(j), i.e. it runs underneath the exponentials of
+//               tile j; PV_j at p_full(j).  K and V ride separate 2-stage rings: the K slot is free again as soon
+//               as S_j has completed, the V slot after PV_j.
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -51,12 +71,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
   uint8_t* sV = sK + kFwdStages * kTk * kHd * 2;            // kFwdStages x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kFwdStages * kTk * kHd * 2);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 1 + kFwdStages;
-  uint64_t* s_full = bars + 1 + 2 * kFwdStages;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = s_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_consumed = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* p_free = bars + 12;   // PV_j complete: P and O are quiescent
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -64,17 +87,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int n_kv = (p.L + kTk - 1) / kTk;
+  long long* tl = (g_fwd_timeline && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                   (warp == 5 || warp == 0))
+                      ? g_fwd_timeline
+                      : nullptr;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < kFwdStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
+    mbar_init(s_consumed, 128);
     mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(p_free, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 256);
@@ -90,60 +120,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       tma_load_3d(sQ, &map_qkv, q_full, h * kHd, q0, b);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % kFwdStages;
-        mbar_wait(&kv_empty[st], ((j / kFwdStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kTk * kHd * 2);
-        tma_load_3d(sK + st * (kTk * kHd * 2), &map_qkv, &kv_full[st], p.D + h * kHd, j * kTk, b);
-        tma_load_3d(sV + st * (kTk * kHd * 2), &map_qkv, &kv_full[st], 2 * p.D + h * kHd, j * kTk, b);
+        const uint32_t ph = ((j / kFwdStages) & 1) ^ 1;
+        mbar_wait(&k_empty[st], ph);
+        mbar_arrive_expect_tx(&k_full[st], kTk * kHd * 2);
+        tma_load_3d(sK + st * (kTk * kHd * 2), &map_qkv, &k_full[st], p.D + h * kHd, j * kTk, b);
+        mbar_wait(&v_empty[st], ph);
+        mbar_arrive_expect_tx(&v_full[st], kTk * kHd * 2);
+        tma_load_3d(sV + st * (kTk * kHd * 2), &map_qkv, &v_full[st], 2 * p.D + h * kHd, j * kTk, b);
       }
     }
   } else if (warp == 5) {
     // whole warp walks the loop; one elected lane issues MMAs / commits inside warp-uniform control flow (under
     // `if (lane == 0)` every UTCHMMA gets wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop)
-    {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kTq, kTk, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kTq, kHd, 0, 1);  // B = V, MN-major
-      const uint64_t dq = make_desc_kmajor(smem_u32(sQ));
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t dk = make_desc_kmajor(smem_u32(sK));
+    constexpr uint32_t idesc_s = make_idesc_bf16(kTq, kTk, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(kTq, kHd, 0, 1);  // B = V, MN-major
+    const uint64_t dq = make_desc_kmajor(smem_u32(sQ));
+    const uint64_t dk0 = make_desc_kmajor(smem_u32(sK));
+    const uint64_t dv0 = make_desc_mnmajor(smem_u32(sV), 64 * 128);
+    mbar_wait(q_full, 0);
+    for (int j = -1; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {  // S_{j+1}: as soon as S_j sits in the softmax threads' registers
+        const int st1 = (j + 1) % kFwdStages;
+        if (j >= 0) mbar_wait(s_consumed, j & 1);
+        mbar_wait(&k_full[st1], ((j + 1) / kFwdStages) & 1);
+        tc_fence_after();
+        const uint64_t dk = dk0 + static_cast<uint64_t>(st1 * (kTk * kHd * 2 >> 4));
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
           umma_commit(s_full);
+          umma_commit(&k_empty[st1]);
         }
         __syncwarp();
       }
-      for (int j = 0; j < n_kv; ++j) {
+      TLF(0, j + 1, 0);
+      if (j >= 0) {  // O (TMEM) += P_j V_j ; the softmax warps have rescaled O beforehand when the row max moved
         const int st = j % kFwdStages;
-        // O (TMEM) += P_j V_j ; the softmax warps have rescaled O beforehand when the row max moved
         mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], (j / kFwdStages) & 1);
         tc_fence_after();
-        const uint64_t dv = make_desc_mnmajor(smem_u32(sV + st * (kTk * kHd * 2)), 64 * 128);
-        const uint32_t acc = j ? 1u : 0u;
+        const uint64_t dv = dv0 + static_cast<uint64_t>(st * (kTk * kHd * 2 >> 4));
         if (elect_one()) {
-          umma_ts(tO, tP, dv, idesc_pv, acc);
+          umma_ts(tO, tP, dv, idesc_pv, j ? 1u : 0u);
 #pragma unroll
           for (int k = 1; k < kTk / 16; ++k) umma_ts(tO, tP + 8 * k, dv + 128 * k, idesc_pv, 1u);
-          umma_commit(&kv_empty[st]);
-        }
-        __syncwarp();
-        if (j + 1 < n_kv) {
-          const int st1 = (j + 1) % kFwdStages;
-          mbar_wait(&kv_full[st1], ((j + 1) / kFwdStages) & 1);
-          tc_fence_after();
-          const uint64_t dk = make_desc_kmajor(smem_u32(sK + st1 * (kTk * kHd * 2)));
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-            umma_commit(s_full);  // also certifies that PV_j has completed: P and O are quiescent
-          }
-        } else {
-          if (elect_one()) umma_commit(o_full);
+          umma_commit(p_free);
+          umma_commit(&v_empty[st]);
         }
         __syncwarp();
       }
+      TLF(0, j + 1, 1);
     }
   } else {
     // ------------------------------ softmax warpgroup ------------------------------
@@ -157,14 +183,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * kTk;
       const bool tail = kv0 + kTk > p.L;
+      TLF(1, j, 0);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      TLF(1, j, 1);
       uint32_t sr[128];
       tmem_ld32(tS + lane_base, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
       tmem_ld32(tS + lane_base + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
       tmem_ld32(tS + lane_base + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
       tmem_ld32(tS + lane_base + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_consumed);  // S_{j+1} may overwrite tS
+      TLF(1, j, 2);
       if (tail) {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
@@ -180,6 +211,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.sl2;
       const bool grow = mx > m + 8.0f;  // first tile: m = -inf -> true
+      bool pv_done = j == 0;            // has this thread observed the completion of PV_{j-1} ?
       if (__any_sync(0xffffffffu, grow)) {
         const float alpha = grow ? fast_exp2(m - mx) : 1.0f;  // exp2(-inf) = 0 on the first tile
         if (grow) {
@@ -187,6 +219,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
           l *= alpha;
         }
         if (j > 0) {  // rescale the O accumulator in TMEM (warp-collective; lanes that did not grow use 1)
+          mbar_wait(p_free, (j - 1) & 1);
+          tc_fence_after();
+          pv_done = true;
 #pragma unroll
           for (int c = 0; c < kHd / 32; ++c) {
             uint32_t o[32];
@@ -199,27 +234,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
           }
         }
       }
+      TLF(1, j, 3);
+      // exponentials in place (S_{j+1} and PV_{j-1} run on the tensor pipe meanwhile)
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c * 16 + 2 * i]), p.sl2, -m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c * 16 + 2 * i + 1]), p.sl2, -m));
-          sum0 += p0;
-          sum1 += p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-        tmem_st8(tP + lane_base + c * 8, pk);
+      for (int i = 0; i < 128; i += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.sl2, -m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.sl2, -m));
+        sum0 += p0;
+        sum1 += p1;
+        sr[i >> 1] = pack_bf16(p0, p1);
       }
       l += sum0 + sum1;
+      TLF(1, j, 4);
+      if (!pv_done) {  // PV_{j-1} has finished reading P_{j-1}
+        mbar_wait(p_free, (j - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st16(tP + lane_base + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[c * 16]));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
+      TLF(1, j, 5);
     }
 
-    mbar_wait(o_full, 0);
+    mbar_wait(p_free, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
     // tcgen05.ld is warp-collective: every lane reads its O row, only valid rows are stored

@@ -47,10 +47,10 @@ struct GemmNtParams {
 };
 
 // Epilogue staging: the 128 x BN accumulator tile leaves through shared memory in column chunks of
-// 128 bytes per row (64 bf16 or 32 fp32 columns): each epilogue thread writes its row into a
-// SWIZZLE_128B [128][128 B] buffer and one thread issues a TMA store (full-line, asynchronous,
+// 128 bytes per row (64 bf16 or 32 fp32 columns): each epilogue warp writes its 32 rows of a chunk into
+// a private SWIZZLE_128B [32][128 B] buffer and issues its own TMA store (full-line, asynchronous,
 // M-tail clipped by the tensor map).  Inputs of the epilogue (residual / GELU pre-activation) arrive
-// the same way through TMA loads, prefetched one chunk ahead.
+// the same way through per-warp TMA loads, fetched while the previous chunk is being computed.
 constexpr int kChunkBytes = kBM * 128;  // 16 KB
 
 template <int EPI>
@@ -75,9 +75,8 @@ struct NtCfg {
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each taking half of a chunk's columns
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, taking alternate column chunks
 constexpr int kNtThreads = 128 + kEpiWarps * 32;
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 // CM > 1: thread-block cluster of CM CTAs working on CM consecutive M-tiles of the same N-tile.  Every CTA loads
 // its own A tile and 1/CM of the shared B tile, multicasting that slice into the shared memory of all CTAs of the
@@ -110,8 +109,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
-  uint64_t* in_full = bars + 2 * kStages + 4;  // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
+  uint64_t* in_full = bars + 2 * kStages + 4;  // [kEpiWarps]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,8 +149,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
-      mbar_init(&in_full[i], 1);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&in_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -255,135 +254,154 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp >= 4 && ET::kTma) {
     // ---------------- epilogue: TMEM -> registers -> swizzled smem -> TMA store ----------------
+    // Every epilogue warp works on its own: the two warps of a TMEM lane quadrant take alternate column chunks of
+    // the tile (all CW columns of their 32 rows), stage them in a private [32][128 B] buffer and issue their own
+    // TMA store / input load.  No cross-warp barrier: while one warp of a sub-partition waits on TMEM, TMA or its
+    // store buffer, the other keeps the FMA / MUFU pipes busy with its GELU.
     constexpr int CW = ET::kCW;
-    constexpr int HW = CW / 2;  // columns per thread: warps w and w+4 share a lane quadrant and split the chunk
     constexpr int kChunks = BN / CW;
+    constexpr int kWarpChunkBytes = 32 * 128;  // 4 KB
     const int q = warp & 3;  // TMEM lane quadrant owned by this warp
     const int half = (warp - 4) >> 2;
-    const int r = q * 32 + lane;
-    const int tid_e = threadIdx.x - 128;
+    const int ew = warp - 4;
+    uint8_t* my_out = stage_out + ew * kWarpChunkBytes;
+    uint8_t* my_out2 = stage_out2 + ew * kWarpChunkBytes;
+    uint8_t* my_in = stage_in + ew * kWarpChunkBytes;
+    uint64_t* my_in_full = &in_full[ew];
+    const uint32_t s_out = smem_u32(my_out), s_out2 = smem_u32(my_out2), s_in = smem_u32(my_in);
     const int total_chunks = my_iters * kChunks;
     auto chunk_coords = [&](int n, int& m0, int& col0) {
       int n0;
       tile_coords(n / kChunks, m0, n0);
+      m0 += q * 32;
       col0 = n0 + (n % kChunks) * CW;
     };
-    if (ET::kHasIn && tid_e == 0 && total_chunks > 0) {  // prefetch the input of chunk 0
+    if (ET::kHasIn && lane == 0 && half < total_chunks) {  // prefetch the input of this warp's first chunk
       int m0, col0;
-      chunk_coords(0, m0, col0);
-      mbar_arrive_expect_tx(&in_full[0], kChunkBytes);
-      tma_load_2d(stage_in, &map_in, &in_full[0], col0, m0);
+      chunk_coords(half, m0, col0);
+      mbar_arrive_expect_tx(my_in_full, kWarpChunkBytes);
+      tma_load_2d(my_in, &map_in, my_in_full, col0, m0);
     }
     int as = 0;
-    uint32_t aphase = 0;
-    for (int n = 0; n < total_chunks; ++n) {
-      const int c = n % kChunks;
-      const int buf = n & 1;
-      int m0, col0;
-      chunk_coords(n, m0, col0);
-      if (c == 0) {
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-      }
-      // accumulator half-chunk -> registers
-      float v[HW];
-      {
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * CW + half * HW;
-        if constexpr (HW == 32) {
-          uint32_t r0[32];
-          tmem_ld32(taddr, r0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
-        } else {
-          uint32_t r0[16];
-          tmem_ld16(taddr, r0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
-        }
-      }
-      if (c == kChunks - 1) {  // the whole accumulator tile has been read out
-        tc_fence_before();
+    uint32_t aphase = 0, in_phase = 0;
+    for (int it = 0; it < my_iters; ++it) {
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      // last chunk of this tile that belongs to this warp (-1: none, e.g. single-chunk tiles on the other parity)
+      int c_last = kChunks - 1;
+      if (((it * kChunks + c_last) & 1) != half) --c_last;
+      if (c_last < 0) {
         __syncwarp();
         if (lane == 0) {
-          if (kPair && crank != 0) mbar_arrive_remote(&tmem_empty[as], 0);  // the leader's MMA warp waits for both CTAs
+          if (kPair && crank != 0) mbar_arrive_remote(&tmem_empty[as], 0);
           else mbar_arrive(&tmem_empty[as]);
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      if (EPI != EPI_DGELU && p.bias != nullptr) {
-#pragma unroll
-        for (int i = 0; i < HW; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + half * HW + i));
-          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+      for (int c = 0; c < kChunks; ++c) {
+        const int n = it * kChunks + c;
+        if ((n & 1) != half) continue;
+        int m0, col0;
+        chunk_coords(n, m0, col0);
+        // accumulator chunk -> registers
+        uint32_t v[CW];
+        {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * CW;
+          tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          if constexpr (CW == 64) tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
         }
-      }
-      // staging buffer `buf` must have been read out by the TMA store issued two chunks ago
-      if (tid_e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      epi_barrier();
-      if (ET::kHasIn) {
-        if (tid_e == 0 && n + 1 < total_chunks) {  // prefetch the next chunk's input (its buffer was consumed at n-1)
-          int m1, c1;
-          chunk_coords(n + 1, m1, c1);
-          mbar_arrive_expect_tx(&in_full[buf ^ 1], kChunkBytes);
-          tma_load_2d(stage_in + (buf ^ 1) * kChunkBytes, &map_in, &in_full[buf ^ 1], c1, m1);
-        }
-        mbar_wait(&in_full[buf], (n >> 1) & 1);
-      }
-      // this thread's four 16-byte slots of row r in the [128][128 B] swizzled staging tile
-      const uint32_t s_out = smem_u32(stage_out + buf * kChunkBytes);
-      const int j0 = half * 4;
-      if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_shared_v4(s_out + sw128_offset(r, j0 + j), pack_bf16(v[8 * j], v[8 * j + 1]),
-                       pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                       pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        if (EPI == EPI_BIAS_GELU) {
-          const uint32_t s_out2 = smem_u32(stage_out2 + buf * kChunkBytes);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_shared_v4(s_out2 + sw128_offset(r, j0 + j), pack_bf16(gelu_exact(v[8 * j]), gelu_exact(v[8 * j + 1])),
-                         pack_bf16(gelu_exact(v[8 * j + 2]), gelu_exact(v[8 * j + 3])),
-                         pack_bf16(gelu_exact(v[8 * j + 4]), gelu_exact(v[8 * j + 5])),
-                         pack_bf16(gelu_exact(v[8 * j + 6]), gelu_exact(v[8 * j + 7])));
-        }
-      } else if (EPI == EPI_DGELU) {
-        const uint32_t s_in = smem_u32(stage_in + buf * kChunkBytes);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 hraw = ld_shared_f4(s_in + sw128_offset(r, j0 + j));
-          const float2 h0 = unpack_bf16(__float_as_uint(hraw.x)), h1 = unpack_bf16(__float_as_uint(hraw.y)),
-                       h2 = unpack_bf16(__float_as_uint(hraw.z)), h3 = unpack_bf16(__float_as_uint(hraw.w));
-          st_shared_v4(s_out + sw128_offset(r, j0 + j),
-                       pack_bf16(v[8 * j + 0] * gelu_exact_grad(h0.x), v[8 * j + 1] * gelu_exact_grad(h0.y)),
-                       pack_bf16(v[8 * j + 2] * gelu_exact_grad(h1.x), v[8 * j + 3] * gelu_exact_grad(h1.y)),
-                       pack_bf16(v[8 * j + 4] * gelu_exact_grad(h2.x), v[8 * j + 5] * gelu_exact_grad(h2.y)),
-                       pack_bf16(v[8 * j + 6] * gelu_exact_grad(h3.x), v[8 * j + 7] * gelu_exact_grad(h3.y)));
-        }
-      } else {  // fp32 outputs: EPI_BIAS_RESID / EPI_F32
-        const uint32_t s_in = smem_u32(stage_in + buf * kChunkBytes);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (EPI == EPI_BIAS_RESID) {
-            const float4 rs = ld_shared_f4(s_in + sw128_offset(r, j0 + j));
-            o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+        if (c == c_last) {  // this warp has read its share of the accumulator tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair && crank != 0) mbar_arrive_remote(&tmem_empty[as], 0);  // the leader's MMA warp waits for both CTAs
+            else mbar_arrive(&tmem_empty[as]);
           }
-          st_shared_v4(s_out + sw128_offset(r, j0 + j), __float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z),
-                       __float_as_uint(o.w));
         }
+        // the staging buffer must have been read out by this warp's previous TMA store
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (ET::kHasIn) mbar_wait(my_in_full, in_phase);
+        __syncwarp();
+        const float* bias = (EPI != EPI_DGELU && p.bias != nullptr) ? p.bias + col0 : nullptr;
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[8 * j + i]);
+            if (bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            st_shared_v4(s_out + sw128_offset(lane, j), pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                         pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            if (EPI == EPI_BIAS_GELU)
+              st_shared_v4(s_out2 + sw128_offset(lane, j), pack_bf16(gelu_exact(x[0]), gelu_exact(x[1])),
+                           pack_bf16(gelu_exact(x[2]), gelu_exact(x[3])), pack_bf16(gelu_exact(x[4]), gelu_exact(x[5])),
+                           pack_bf16(gelu_exact(x[6]), gelu_exact(x[7])));
+          }
+        } else if (EPI == EPI_DGELU) {
+          uint32_t hr[32];  // pre-activations of this row: 64 bf16
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 hraw = ld_shared_f4(s_in + sw128_offset(lane, j));
+            hr[4 * j] = __float_as_uint(hraw.x); hr[4 * j + 1] = __float_as_uint(hraw.y);
+            hr[4 * j + 2] = __float_as_uint(hraw.z); hr[4 * j + 3] = __float_as_uint(hraw.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 h0 = unpack_bf16(hr[4 * j]), h1 = unpack_bf16(hr[4 * j + 1]), h2 = unpack_bf16(hr[4 * j + 2]),
+                         h3 = unpack_bf16(hr[4 * j + 3]);
+            st_shared_v4(s_out + sw128_offset(lane, j),
+                         pack_bf16(__uint_as_float(v[8 * j + 0]) * gelu_exact_grad(h0.x),
+                                   __uint_as_float(v[8 * j + 1]) * gelu_exact_grad(h0.y)),
+                         pack_bf16(__uint_as_float(v[8 * j + 2]) * gelu_exact_grad(h1.x),
+                                   __uint_as_float(v[8 * j + 3]) * gelu_exact_grad(h1.y)),
+                         pack_bf16(__uint_as_float(v[8 * j + 4]) * gelu_exact_grad(h2.x),
+                                   __uint_as_float(v[8 * j + 5]) * gelu_exact_grad(h2.y)),
+                         pack_bf16(__uint_as_float(v[8 * j + 6]) * gelu_exact_grad(h3.x),
+                                   __uint_as_float(v[8 * j + 7]) * gelu_exact_grad(h3.y)));
+          }
+        } else {  // fp32 outputs: EPI_BIAS_RESID / EPI_F32 (32 columns per chunk)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (bias != nullptr) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + 4 * j));
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            if (EPI == EPI_BIAS_RESID) {
+              const float4 rs = ld_shared_f4(s_in + sw128_offset(lane, j));
+              o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+            }
+            st_shared_v4(s_out + sw128_offset(lane, j), __float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z),
+                         __float_as_uint(o.w));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (ET::kHasIn) {  // the input buffer has been consumed: fetch this warp's next chunk
+            const int n1 = n + 2;
+            if (n1 < total_chunks) {
+              int m1, c1;
+              chunk_coords(n1, m1, c1);
+              mbar_arrive_expect_tx(my_in_full, kWarpChunkBytes);
+              tma_load_2d(my_in, &map_in, my_in_full, c1, m1);
+            }
+          }
+          tma_store_2d(&map_out, my_out, col0, m0);
+          if (EPI == EPI_BIAS_GELU) tma_store_2d(&map_out2, my_out2, col0, m0);
+          tma_store_commit();
+        }
+        in_phase ^= 1;
       }
-      fence_proxy_async_smem();
-      epi_barrier();
-      if (tid_e == 0) {
-        tma_store_2d(&map_out, stage_out + buf * kChunkBytes, col0, m0);
-        if (EPI == EPI_BIAS_GELU) tma_store_2d(&map_out2, stage_out2 + buf * kChunkBytes, col0, m0);
-        tma_store_commit();
-      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (tid_e == 0) tma_store_wait0();
+    if (lane == 0) tma_store_wait0();
   } else if (warp >= 8) {
     // direct-store epilogue uses warps 4-7 only; these warps just keep the tmem_empty arrival count
     int as = 0;
@@ -675,16 +693,16 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
   if (ET::kTma) {
     const uint64_t esz = ET::kF32Out ? 4 : 2;
     void* outp = ET::kF32Out ? static_cast<void*>(p.out_f32) : static_cast<void*>(p.out_bf16);
-    if (int e = make_tmap_2d(&em.out, outp, ET::kF32Out, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * esz, ET::kCW, kBM))
+    if (int e = make_tmap_2d(&em.out, outp, ET::kF32Out, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * esz, ET::kCW, 32))
       return e;
     if (ET::kTwoOut)
-      if (int e = make_tmap_2d(&em.out2, p.out2_bf16, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 2, ET::kCW, kBM))
+      if (int e = make_tmap_2d(&em.out2, p.out2_bf16, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * 2, ET::kCW, 32))
         return e;
     if (EPI == EPI_BIAS_RESID)
-      if (int e = make_tmap_2d(&em.in, p.resid, true, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 4, ET::kCW, kBM))
+      if (int e = make_tmap_2d(&em.in, p.resid, true, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 4, ET::kCW, 32))
         return e;
     if (EPI == EPI_DGELU)
-      if (int e = make_tmap_2d(&em.in, p.aux, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 2, ET::kCW, kBM))
+      if (int e = make_tmap_2d(&em.in, p.aux, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 2, ET::kCW, 32))
         return e;
   }
   static bool attr_done = false;
