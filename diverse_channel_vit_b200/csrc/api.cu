@@ -223,6 +223,13 @@ int dcv_gemm_nn(const void* A, int lda, const void* B, int ldb, int M, int N, in
   return gemm_nt(A, lda, B, ldb, M, N, K, epilogue, nullptr, out, nullptr, nullptr, aux, ldo, true, ST(stream));
 }
 
+int dcv_gemm_nn_delta(const void* dY, int lda, const void* W, int ldb, int M, int N, int K, void* dO, const void* O,
+                      float* delta, int L, void* stream) {
+  if (!dY || !W || !dO || !O || !delta) return set_error(DCV_ERR_INVALID, "dcv_gemm_nn_delta: null pointer");
+  return gemm_nt(dY, lda, W, ldb, M, N, K, 6 /* EPI_DELTA */, nullptr, dO, nullptr, nullptr, O, N, true, ST(stream), 0, 0,
+                 nullptr, 0, delta, L);
+}
+
 int dcv_gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
                 int accumulate, int splits, void* stream) {
   if (!A || !B || !C) return set_error(DCV_ERR_INVALID, "dcv_gemm_tn: null operand");

@@ -534,7 +534,7 @@ int debug_attn_timeline(long long* buf) {
 }
 
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
-             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only) {
+             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only, bool delta_ready) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(DCV_ERR_INVALID, "attn_bwd: empty problem");
   const int D = H * kHd;
   const int Lp = (L + 127) / 128 * 128;
@@ -556,7 +556,9 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   }
   {
     ProfScope prof(PT_ATTN_BWD_PREP, st);
-    if (cls_only) {
+    if (delta_ready) {
+      // produced by the projection-dgrad GEMM epilogue
+    } else if (cls_only) {
       attn_bwd_prep_cls_kernel<<<B * H, 32, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(o),
                                                      reinterpret_cast<const __nv_bfloat16*>(dO), delta, B, L, H, Lp);
     } else {
@@ -587,7 +589,7 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
         dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, scale);
     DCV_CUDA(cudaGetLastError());
   }
-  count_launch(3);
+  count_launch(delta_ready ? 2 : 3);
   return 0;
 }
 

@@ -28,6 +28,8 @@ enum GemmEpilogue : int {
   EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux)
   EPI_F32 = 4,         // out_f32 = acc (+ bias)
   EPI_EMBED = 5,       // out_f32[(m / T) * L + 1 + m % T][:] = acc + addend[m % T][:]   (patch embedding)
+  EPI_DELTA = 6,       // out_bf16 = dO = acc ; delta[b, h, q] = sum over head h's 64 columns of bf16(dO) * aux (aux = the
+                       // attention output O): the softmax-backward row term, one column chunk == one head
 };
 
 struct GemmNtParams {
@@ -44,6 +46,9 @@ struct GemmNtParams {
   // tensor (row 0 of every image is the CLS token, written elsewhere); addend fp32 [T, ldo]
   int map_T, map_L;
   const float* addend;
+  // EPI_DELTA: rows m = (image b, query q) with q in [0, seq_L); delta fp32 [B, N/64, seq_Lp]
+  float* delta;
+  int seq_L, seq_Lp;
 };
 
 // Epilogue staging: the 128 x BN accumulator tile leaves through shared memory in column chunks of
@@ -57,7 +62,7 @@ template <int EPI>
 struct EpiTraits {
   static constexpr bool kTma = EPI != EPI_EMBED;
   static constexpr bool kF32Out = EPI == EPI_BIAS_RESID || EPI == EPI_F32 || EPI == EPI_EMBED;
-  static constexpr bool kHasIn = EPI == EPI_BIAS_RESID || EPI == EPI_DGELU;
+  static constexpr bool kHasIn = EPI == EPI_BIAS_RESID || EPI == EPI_DGELU || EPI == EPI_DELTA;
   static constexpr bool kTwoOut = EPI == EPI_BIAS_GELU;
   static constexpr int kCW = kF32Out ? 32 : 64;  // columns per chunk
   // out[2] (+ out2[2]) (+ in[2])
@@ -363,6 +368,29 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                    __uint_as_float(v[8 * j + 5]) * gelu_exact_grad(h2.y)),
                          pack_bf16(__uint_as_float(v[8 * j + 6]) * gelu_exact_grad(h3.x),
                                    __uint_as_float(v[8 * j + 7]) * gelu_exact_grad(h3.y)));
+          }
+        } else if (EPI == EPI_DELTA) {
+          float dsum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 oraw = ld_shared_f4(s_in + sw128_offset(lane, j));
+            const uint32_t ow[4] = {__float_as_uint(oraw.x), __float_as_uint(oraw.y), __float_as_uint(oraw.z),
+                                    __float_as_uint(oraw.w)};
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pk[i] = pack_bf16(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1]));
+              const float2 g2 = unpack_bf16(pk[i]), o2 = unpack_bf16(ow[i]);  // the rounded dO the attention kernel reads
+              dsum = fmaf(g2.x, o2.x, dsum);
+              dsum = fmaf(g2.y, o2.y, dsum);
+            }
+            st_shared_v4(s_out + sw128_offset(lane, j), pk[0], pk[1], pk[2], pk[3]);
+          }
+          const int m = m0 + lane;
+          if (m < p.M) {
+            const int bi = m / p.seq_L;
+            const int qi = m - bi * p.seq_L;
+            p.delta[(static_cast<size_t>(bi) * (p.N >> 6) + (col0 >> 6)) * p.seq_Lp + qi] = dsum;
           }
         } else {  // fp32 outputs: EPI_BIAS_RESID / EPI_F32 (32 columns per chunk)
 #pragma unroll
@@ -701,7 +729,7 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
     if (EPI == EPI_BIAS_RESID)
       if (int e = make_tmap_2d(&em.in, p.resid, true, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 4, ET::kCW, 32))
         return e;
-    if (EPI == EPI_DGELU)
+    if (EPI == EPI_DGELU || EPI == EPI_DELTA)
       if (int e = make_tmap_2d(&em.in, p.aux, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 2, ET::kCW, 32))
         return e;
   }
@@ -739,6 +767,7 @@ static int dispatch_nt_epi(int epi, bool b_mn, const CUtensorMap& ma, const CUte
       switch (epi) {
         case EPI_BIAS: return launch_nt<BN, EPI_BIAS, true, MODE>(ma, mb, p, st);
         case EPI_DGELU: return launch_nt<BN, EPI_DGELU, true, MODE>(ma, mb, p, st);
+        case EPI_DELTA: return launch_nt<BN, EPI_DELTA, true, MODE>(ma, mb, p, st);
         case EPI_F32: return launch_nt<BN, EPI_F32, true, MODE>(ma, mb, p, st);
       }
     }
@@ -771,7 +800,7 @@ static int g_nt_pair = 0;
 // b_mn = false: B is [N][K] (K contiguous);  b_mn = true: B is [K][N] (N contiguous)
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
             void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st,
-            int map_T, int map_L, const float* addend, int ldin) {
+            int map_T, int map_L, const float* addend, int ldin, float* delta, int seq_L) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(DCV_ERR_INVALID, "gemm_nt: empty problem %dx%dx%d", M, N, K);
   if (K % 8 || lda % 8 || ldb % 8 || ldo % 8)
     return set_error(DCV_ERR_UNSUPPORTED, "gemm_nt: K/lda/ldb/ldo must be multiples of 8 (16-byte rows)");
@@ -801,9 +830,12 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   p.resid = resid;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
   p.map_T = map_T; p.map_L = map_L; p.addend = addend;
+  p.delta = delta; p.seq_L = seq_L; p.seq_Lp = (seq_L + 127) / 128 * 128;
+  if (epi == EPI_DELTA && (!b_mn || !aux || !delta || seq_L <= 0 || M % seq_L))
+    return set_error(DCV_ERR_INVALID, "gemm_nn: EPI_DELTA needs aux (O), delta, seq_L > 0 dividing M");
   if (epi == EPI_EMBED && (!addend || map_T <= 0 || map_L <= map_T || M % map_T))
     return set_error(DCV_ERR_INVALID, "gemm_nt: EPI_EMBED needs addend, T>0, L>T, M %% T == 0");
-  if ((epi == EPI_BIAS_GELU && !out2) || (epi == EPI_BIAS_RESID && !resid) || (epi == EPI_DGELU && !aux) || !out)
+  if ((epi == EPI_BIAS_GELU && !out2) || (epi == EPI_BIAS_RESID && !resid) || ((epi == EPI_DGELU || epi == EPI_DELTA) && !aux) || !out)
     return set_error(DCV_ERR_INVALID, "gemm_nt: missing buffer for epilogue %d", epi);
   if (pair) {
     switch (bn) {

@@ -68,7 +68,8 @@ int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
 // ---- gemm.cu ----
 int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const float* bias,
             void* out, void* out2, const float* resid, const void* aux, int ldo, bool b_mn, cudaStream_t st,
-            int map_T = 0, int map_L = 0, const float* addend = nullptr, int ldin = 0);
+            int map_T = 0, int map_L = 0, const float* addend = nullptr, int ldin = 0, float* delta = nullptr,
+            int seq_L = 0);
 int gemm_tn(const void* A, int lda, const void* B, int ldb, int M, int Nout, int Kout, float* C, int ldc,
             int accumulate, int splits, cudaStream_t st);
 void debug_set_tn_desc(int lbo, int sbo);
@@ -80,8 +81,11 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
              int q_tiles = 0);
 // cls_only: dO is compact [B, D] (gradient of the CLS rows of o, every other row being zero); only query tile 0 is
 // visited, dK / dV / dQ are still produced for all rows
+// delta_ready: delta[b,h,q] = sum_d dO*O was already produced (epilogue of the projection dgrad GEMM, EPI_DELTA; pad
+// rows [L, Lp) zero); otherwise a prep kernel computes it here
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
-             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only = false);
+             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only = false,
+             bool delta_ready = false);
 
 int debug_attn_timeline(long long* buf);
 

@@ -6,7 +6,7 @@
 
 namespace dcv {
 
-enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_DGELU = 3, EPI_F32 = 4, EPI_EMBED = 5 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_DGELU = 3, EPI_F32 = 4, EPI_EMBED = 5, EPI_DELTA = 6 };
 
 #define DCV_TRY(expr)            \
   do {                           \
@@ -52,9 +52,13 @@ int block_bwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts
   // dres += LN2'(dv); column sums of the result = d proj bias
   DCV_TRY(ln_bwd(ws.dv, a.x_mid, a.mean2, a.rstd2, p.ln2_w, dres, dres_bf16, g.ln2_w, g.ln2_b, g.proj_b, M, D, st));
   // ---- attention branch:  x_mid = x_in + proj(attn(qkv(LN1 x_in))) ----
-  DCV_TRY(gemm_nt(dres_bf16, D, p.proj_w, D, M, D, D, EPI_BIAS, nullptr, ws.d_o, nullptr, nullptr, nullptr, D, true, st));
+  // dO = dres Wproj, with delta[b,h,q] = sum_d dO*O (the softmax-backward row term) from the same epilogue
+  if (d.L % 128)
+    DCV_CUDA(cudaMemsetAsync(ws.delta, 0, static_cast<size_t>(d.B) * d.H * ((d.L + 127) / 128 * 128) * sizeof(float), st));
+  DCV_TRY(gemm_nt(dres_bf16, D, p.proj_w, D, M, D, D, EPI_DELTA, nullptr, ws.d_o, nullptr, nullptr, a.o, D, true, st, 0, 0,
+                  nullptr, 0, ws.delta, d.L));
   DCV_TRY(gemm_tn(dres_bf16, D, a.o, D, M, D, D, g.proj_w, D, 1, 0, st));
-  DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st));
+  DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st, false, true));
   DCV_TRY(gemm_nt(ws.dqkv, 3 * D, p.qkv_w, D, M, D, 3 * D, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
   DCV_TRY(gemm_tn(ws.dqkv, 3 * D, a.u, D, M, 3 * D, D, g.qkv_w, D, 1, 0, st));
   DCV_TRY(colsum_bf16(ws.dqkv, g.qkv_b, M, 3 * D, 3 * D, st));

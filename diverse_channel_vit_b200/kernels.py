@@ -59,6 +59,19 @@ def gemm_nn(a, b, epilogue=EPI_BIAS, out=None, aux=None):
     return out
 
 
+def gemm_nn_delta(dy, w, o, B, L):
+    """dO = dy[M,K] @ w[K,N] (bf16) and delta[B, N/64, Lp] = per-head rowsum(dO * o); M = B*L."""
+    _req(dy, torch.bfloat16, "dy"); _req(w, torch.bfloat16, "w"); _req(o, torch.bfloat16, "o")
+    M, K = dy.shape
+    N = w.shape[1]
+    assert M == B * L and o.shape == (M, N) and o.is_contiguous()
+    d_o = torch.empty((M, N), device=dy.device, dtype=torch.bfloat16)
+    delta = torch.zeros((B, N // 64, lpad(L)), device=dy.device, dtype=torch.float32)
+    check(_lib.lib().dcv_gemm_nn_delta(ptr(dy), dy.stride(0), ptr(w), w.stride(0), M, N, K, ptr(d_o), ptr(o), ptr(delta),
+                                       L, stream_ptr()), "dcv_gemm_nn_delta")
+    return d_o, delta
+
+
 def gemm_tn(a, b, out=None, accumulate=True, splits=0):
     """out[Nout,Kout] (+)= a[M,Nout]^T @ b[M,Kout]; fp32 output."""
     _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")

@@ -60,6 +60,13 @@ int dcv_gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, in
 int dcv_gemm_nn(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, void* out,
                 const void* aux, int ldo, void* stream);
 
+/* Projection input gradient fused with the softmax-backward row term: dO[M,N] = dY[M,K] * W[K,N] (bf16 out) and
+ * delta[b, h, q] = sum over head h's 64 columns of dO * O, rows m = b*L + q, delta fp32 [B, N/64, Lp]
+ * (Lp = L rounded up to 128; the caller zero-fills the pad rows).  Replaces the autograd backward of
+ * models/vit.py:140-141 (proj Linear dgrad) plus the rowsum(dO o O) pass of the attention backward. */
+int dcv_gemm_nn_delta(const void* dY, int lda, const void* W, int ldb, int M, int N, int K, void* dO, const void* O,
+                      float* delta, int L, void* stream);
+
 /* C[Nout,Kout] (+)= A[M,Nout]^T * B[M,Kout]; A, B bf16 row-major, C fp32.
  * accumulate=1: split-K atomic accumulation into C (caller zero-fills or holds a
  * running gradient); accumulate=0: plain store, single split.  splits<=0: auto.

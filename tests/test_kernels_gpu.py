@@ -59,6 +59,19 @@ def test_gemm_nn_dgrad(K, M, N, Kd):
     assert rel_l2(dg, hf.grad) < 1e-2
 
 
+@pytest.mark.parametrize("B,L,H", [(2, 197, 6), (3, 81, 3), (1, 1569, 6)])
+def test_gemm_nn_delta(K, B, L, H):
+    """projection dgrad with the fused softmax-backward row term delta = rowsum_head(dO * O)"""
+    D = H * 64
+    dy, w, o = _bf(B * L, D, seed=11), _bf(D, D, scale=0.05, seed=12), _bf(B * L, D, seed=13)
+    d_o, delta = K.gemm_nn_delta(dy, w, o, B, L)
+    ref = dy.float() @ w.float()
+    assert rel_l2(d_o, ref) < 1e-2
+    dref = (d_o.float() * o.float()).reshape(B, L, H, 64).sum(-1).permute(0, 2, 1)  # from the rounded dO, as the kernel
+    assert rel_l2(delta[:, :, :L], dref) < 1e-5
+    assert delta[:, :, L:].abs().max().item() == 0.0
+
+
 @pytest.mark.parametrize("M,Nout,Kout", [(64, 128, 192), (5000, 1152, 384), (3001, 384, 1536), (515, 64, 64), (999, 384, 256)])
 def test_gemm_tn_wgrad(K, M, Nout, Kout):
     a, b = _bf(M, Nout, seed=9), _bf(M, Kout, seed=10)

@@ -3,7 +3,9 @@
 import sys
 sys.path.insert(0, ".")
 import torch
-from diverse_channel_vit_b200 import kernels as K
+from diverse_channel_vit_b200 import kernels as K, _lib
+import os
+if os.environ.get('DCV_CM'): _lib.lib().dcv_debug_set_nt_cluster(int(os.environ['DCV_CM']))
 M, D, F = 50208, 384, 1536
 dev = "cuda"
 def bf(*s): return (torch.randn(*s, device=dev) * 0.5).bfloat16()
