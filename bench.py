@@ -461,7 +461,7 @@ def ours(args, wname):
     cpu = None
     if world == 1 and not args.no_cpu:
         bb = 4 if w["img"] >= 224 else 32
-        ips, secs, cores, sample = cpu_reference_run(wname, 2, 1, bb)
+        ips, secs, cores, sample = cpu_reference_run(wname, 12, 1, bb)  # ~10-15 s of host work
         cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     # ---- PyTorch eager on the same GPU (library kernels), rank 0, N == 1 only ----
