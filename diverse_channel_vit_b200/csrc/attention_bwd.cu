@@ -18,7 +18,8 @@
 // owns the query columns [64g, 64g+64) of every S^T / dP^T tile (TMEM lane = key row = 32*(warp%4)+lane);
 // warp 8 = TMA producer; warp 9 = front MMA issuer (S, dP; owns TMEM); warp 10 = back MMA issuer (dK, dV, dQ);
 // warps 12-15 drain dQ.
-// TMEM columns: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,448) | P^T bf16 [448,512)
+// TMEM columns: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ fp32 / P^T bf16 (time-shared) [384,448)
+//               | K bf16 [448,480) | V bf16 [480,512)   (K, V: A operands of the S^T / dP^T TS-MMAs, copied once per CTA)
 #include "common.cuh"
 #include "host.h"
 
@@ -79,19 +80,19 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
 struct BwdBars {
   uint64_t kv_full, q_full[kQStages], q_empty[kQStages], do_full[2], do_empty[2];
   uint64_t s_full, dp_full, s_consumed, dp_consumed, phase_done, p_free, ds_free[2];
-  uint64_t dq_full, dq_empty, dkv_full;
+  uint64_t dq_full, dq_empty, dkv_full, kv_tmem;
   uint32_t tmem_slot;
 };
 
 // One software-pipelined phase of a compute thread (key row r, query columns [32cg, 32cg+32) of the tile):
 //   A part (tile i)  : P^T = exp2(S^T * sl2 - lse2[q])                   -> bf16 into TMEM at the end of the phase
-//   B part (tile i-1): dS^T = P^T o (dP^T - delta[q]), P^T re-read from TMEM -> bf16 into the swizzled smem tile
+//   B part (tile i-1): dS^T = P^T o (dP^T - delta[q]), P^T kept packed in registers -> bf16 into the swizzled smem tile
 // The B part's FMA-pipe work fills the issue slots the A part leaves while it waits on the MUFU; four compute warps
 // per SM sub-partition hide the dependent-instruction latency.
 template <bool HAS_A, bool HAS_B>
 __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_base, BwdBars* bars, uint8_t* sStat,
                                           uint8_t* sdS, uint32_t tS, uint32_t tdP, uint32_t tP, float sl2, bool zero_row,
-                                          long long* tl) {
+                                          uint32_t (&pkeep)[16], long long* tl) {
   uint32_t s[32];
   TL(1 + cg, i, 0);
   if (HAS_A) {
@@ -117,11 +118,8 @@ __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_ba
   const uint32_t s_lse = smem_u32(sStat + (i % kQStages) * kStatBytes) + cg * 128;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {  // 16 query columns per step
-    uint32_t d[16], pp[8];
-    if (HAS_B) {
-      tmem_ld16(tdP + lane_base + cg * 32 + 16 * c, d);
-      tmem_ld8(tP + lane_base + cg * 16 + 8 * c, pp);
-    }
+    uint32_t d[16];
+    if (HAS_B) tmem_ld16(tdP + lane_base + cg * 32 + 16 * c, d);
     if (HAS_A) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -141,8 +139,8 @@ __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_ba
 #pragma unroll
       for (int v = 0; v < 2; ++v) {  // 8 queries -> one 16-byte slot of the swizzled dS^T tile
         const float4 da = ld_shared_f4(s_del + (16 * c + 8 * v) * 4), db = ld_shared_f4(s_del + (16 * c + 8 * v + 4) * 4);
-        const float2 p0 = unpack_bf16(pp[4 * v + 0]), p1 = unpack_bf16(pp[4 * v + 1]);
-        const float2 p2 = unpack_bf16(pp[4 * v + 2]), p3 = unpack_bf16(pp[4 * v + 3]);
+        const float2 p0 = unpack_bf16(pkeep[8 * c + 4 * v + 0]), p1 = unpack_bf16(pkeep[8 * c + 4 * v + 1]);
+        const float2 p2 = unpack_bf16(pkeep[8 * c + 4 * v + 2]), p3 = unpack_bf16(pkeep[8 * c + 4 * v + 3]);
         const float e0 = p0.x * (__uint_as_float(d[8 * v + 0]) - da.x);
         const float e1 = p0.y * (__uint_as_float(d[8 * v + 1]) - da.y);
         const float e2 = p1.x * (__uint_as_float(d[8 * v + 2]) - da.z);
@@ -158,15 +156,15 @@ __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_ba
   }
   TL(1 + cg, i, 3);
   if (HAS_A) {
-    if (i > 0) {  // dV_{i-1} has finished reading P_{i-1}
-      mbar_wait(&bars->p_free, (i - 1) & 1);
-      tc_fence_after();
-    }
-    uint32_t pk[16];
+    // P^T shares its TMEM columns with the dQ accumulator: dV_{i-1} must have read P_{i-1} and the drain warps
+    // must have taken dQ_{i-2} out before P_i goes in (dQ_{i-1} is issued behind dV_i by the same thread)
+    if (i > 0) mbar_wait(&bars->p_free, (i - 1) & 1);
+    if (i > 1) mbar_wait(&bars->dq_empty, (i - 2) & 1);
+    if (i > 0) tc_fence_after();
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      pk[j] = zero_row ? 0u : pack_bf16(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1]));
-    tmem_st16(tP + lane_base + cg * 16, pk);
+      pkeep[j] = zero_row ? 0u : pack_bf16(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1]));
+    tmem_st16(tP + lane_base + cg * 16, pkeep);
     tmem_st_wait();
   }
   if (HAS_B) fence_proxy_async_smem();
@@ -226,6 +224,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_empty, 128);  // the four drain warps
     mbar_init(&bars->dkv_full, 1);
+    mbar_init(&bars->kv_tmem, 512);
     fence_barrier_init();
   }
   if (warp == kWarpFront) tmem_alloc(&bars->tmem_slot, 512);
@@ -233,8 +232,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
+  // P^T (bf16) and the dQ accumulator time-share columns [384,448); K and V sit in TMEM as A operands of S^T / dP^T
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
-                 tdQ = tmem_base + 384, tP = tmem_base + 448;
+                 tdQ = tmem_base + 384, tP = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
 
   if (warp >= kWarpTma && warp < kWarpDrain0) {
     setmaxnreg_dec<40>();
@@ -266,11 +266,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       // A single warp runs its dependent instruction stream at ~5 clk per instruction, so the issue work of one
       // (q-tile, k-tile) pair is split over two warps (this one and the back issuer, warp 10).
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
-      const uint64_t dK_k = make_desc_kmajor(smem_u32(sK));
-      const uint64_t dV_k = make_desc_kmajor(smem_u32(sV));
       const uint64_t dQ_k0 = make_desc_kmajor(smem_u32(sQ));     // + stage * (16 KB >> 4)
       const uint64_t dO_k0 = make_desc_kmajor(smem_u32(sdO));
-      mbar_wait(&bars->kv_full, 0);
+      mbar_wait(&bars->kv_tmem, 0);  // K, V copied into TMEM by the compute warps
+      tc_fence_after();
       for (int i = -1; i < n_q; ++i) {
         if (i + 1 < n_q) {
           const int s1 = (i + 1) % kQStages;
@@ -280,7 +279,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const uint64_t dQn_k = dQ_k0 + static_cast<uint64_t>(s1 * (kTile16K >> 4));
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tS, dK_k + 2 * k, dQn_k + 2 * k, id_s, k ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_ts(tS, tK + 8 * k, dQn_k + 2 * k, id_s, k ? 1u : 0u);
             umma_commit(&bars->s_full);
           }
           __syncwarp();
@@ -293,7 +292,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const uint64_t dO_k = dO_k0 + static_cast<uint64_t>((i & 1) * (kTile16K >> 4));
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tdP, dV_k + 2 * k, dO_k + 2 * k, id_s, k ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_ts(tdP, tV + 8 * k, dO_k + 2 * k, id_s, k ? 1u : 0u);
             umma_commit(&bars->dp_full);
             umma_commit(&bars->do_empty[i & 1]);
           }
@@ -409,9 +408,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     const bool kv_ok = kv0 + r < p.L;
 
-    bwd_phase<true, false>(0, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, tl);
-    for (int i = 1; i < n_q; ++i) bwd_phase<true, true>(i, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, tl);
-    bwd_phase<false, true>(n_q, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, tl);
+    {  // K (column groups 0, 1) and V (2, 3) -> TMEM: 16 packed columns = 32 head-dim elements of row r per thread
+      mbar_wait(&bars->kv_full, 0);
+      const uint32_t src = smem_u32((cg < 2) ? sK : sV);
+      uint32_t w[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 x = ld_shared_f4(src + sw128_offset(r, 4 * (cg & 1) + c));
+        w[4 * c] = __float_as_uint(x.x); w[4 * c + 1] = __float_as_uint(x.y);
+        w[4 * c + 2] = __float_as_uint(x.z); w[4 * c + 3] = __float_as_uint(x.w);
+      }
+      tmem_st16(((cg < 2) ? tK : tV) + lane_base + 16 * (cg & 1), w);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars->kv_tmem);
+    }
+    uint32_t pkeep[16];  // P^T of the previous tile, packed bf16 (B part of the next phase)
+    bwd_phase<true, false>(0, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
+    for (int i = 1; i < n_q; ++i)
+      bwd_phase<true, true>(i, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
+    bwd_phase<false, true>(n_q, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
 
     // ---- epilogue: dK (x scale) and dV rows of this key tile; column group cg writes d columns [16cg, 16cg+16) ----
     mbar_wait(&bars->dkv_full, 0);
