@@ -447,6 +447,27 @@ def ours(args, wname):
     elif top is not None:
         roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": float(peaks.get("hbm_gbs", 6650.0)),
                 "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
+    # memory-bound kernel classes: algorithmic bytes per STEP / summed CUDA-event time, against the
+    # measured HBM copy bandwidth.  Full-size calls only are counted (the last block's CLS-row calls move KBs).
+    hbm_peak = float(peaks.get("hbm_gbs", 6550.0))
+    F = 4 * D
+    by = {k: 0.0 for k in ("ln_fwd", "ln_bwd", "colsum", "attn_bwd_fin", "im2col", "tdl", "embed_bwd")}
+    for nb, Lc in subs:
+        M = nb * Lc
+        Tc = Lc - 1
+        by["ln_fwd"] += (2 * (depth - 1) + 1) * M * D * (4 + 2)
+        by["ln_bwd"] += (2 * (depth - 1) + 1) * M * D * 16
+        by["colsum"] += (depth - 1) * M * F * 2 + depth * M * 3 * D * 2
+        by["attn_bwd_fin"] += depth * M * D * (4 + 2)
+        by["im2col"] += nb * Tc * (w["patch"] ** 2) * (4 + 6)
+        by["tdl"] += nb * Tc * D * 4
+        by["embed_bwd"] += nb * (2 * Lc * D * 4 + Tc * D * 2) + nb * Lc * D * 4  # dY pass + batch sum of the token gradient
+    hbm_kernels = {}
+    for k, nbytes in by.items():
+        if k in prof and prof[k]["ms_per_step"] > 0:
+            gbs = nbytes / (prof[k]["ms_per_step"] * 1e-3) / 1e9
+            hbm_kernels[k] = {"GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 3),
+                              "ms_per_step": round(prof[k]["ms_per_step"], 4)}
     attn_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("attn_fwd", "attn_bwd", "attn_bwd_prep", "attn_bwd_fin"))
     attn_tf = (fl["attn_fwd"] + fl["attn_bwd"]) / (attn_ms * 1e-3) / 1e12 if attn_ms else None
     gemm_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("gemm_nt", "gemm_nn", "gemm_tn"))
@@ -497,6 +518,7 @@ def ours(args, wname):
         "kernel_breakdown_dcs_ms_per_step": dict(sorted(prof_dcs.items(), key=lambda kv: -kv[1])),
         "attn_tflops": attn_tf, "attn_frac_of_peak": (attn_tf / peak_tf) if attn_tf else None,
         "gemm_tflops": gemm_tf, "gemm_frac_of_peak": (gemm_tf / peak_tf) if gemm_tf else None,
+        "hbm_kernels": hbm_kernels,
         "cpu_baseline": cpu,
         "torch_eager_gpu": eager,
     }

@@ -303,6 +303,21 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// read a float at the same shared-memory offset in CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_smem_ptr, uint32_t rank) {
+  float v;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+      "ld.shared::cluster.f32 %0, [ra];\n\t"
+      "}\n"
+      : "=f"(v)
+      : "r"(smem_u32(local_smem_ptr)), "r"(rank)
+      : "memory");
+  return v;
+}
+
 // ---- cta_group::2: one MMA spanning the CTA pair of a 2-CTA cluster (M = 256: each CTA supplies its 128 rows of A
 // and half of B from its own shared memory and receives its 128 accumulator rows in its own TMEM) ----
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one full warp in EACH CTA

@@ -125,8 +125,10 @@ __global__ void embed_addend_kernel(const float* __restrict__ bias, const float*
 //   pos_sum = sum_c |S_c|^2 - sum_i |f_i|^2        neg_sum = |sum_c S_c|^2 - sum_c |S_c|^2
 // which equals the masked Gram sums of models/loss_fn.py:36-48 without the B x T x T matrix.
 //
-// tdl_sum_kernel: one CTA per (b, c); warps stride over the channel's N tokens; y is recovered
-// from the stored token as tokens - addend + bias (the GEMM epilogue added addend).
+// tdl_sum_kernel: one CTA -- or one thread-block cluster of `split` CTAs, each taking a slice of the tokens, when
+// B*C' alone would not fill the 148 SMs -- per (b, c); warps stride over the channel's N tokens; y is recovered
+// from the stored token as tokens - addend + bias (the GEMM epilogue added addend).  The cluster's partial sums are
+// combined by its rank-0 CTA through distributed shared memory in rank order: no atomics, deterministic.
 //   S [B, C', D] fp32, Q [B, C'] = sum_i |f_i|^2, rnorm [B, T] = 1 / max(|y_i|, eps)
 // ---------------------------------------------------------------------------------
 constexpr int kTdlWarps = 8;
@@ -134,11 +136,15 @@ constexpr int kTdlWarps = 8;
 template <int NV>
 __global__ void __launch_bounds__(kTdlWarps * 32)
 tdl_sum_kernel(const float* __restrict__ tokens, const float* __restrict__ addend, const float* __restrict__ bias,
-               float* __restrict__ S, float* __restrict__ Q, float* __restrict__ rnorm, int Cs, int N, int D) {
+               float* __restrict__ S, float* __restrict__ Q, float* __restrict__ rnorm, int Cs, int N, int D,
+               int split) {
   extern __shared__ __align__(16) float red[];  // [kTdlWarps][D] + [kTdlWarps]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 2;
-  const int bc = blockIdx.x;
+  const int bc = blockIdx.x / split;
+  const int rank = blockIdx.x - bc * split;  // == %cluster_ctarank
+  const int per = (N + split - 1) / split;
+  const int p_lo = rank * per, p_hi = min(N, p_lo + per);
   const int b = bc / Cs, c = bc - b * Cs;
   const int T = Cs * N;
   float4 bi[NV], acc[NV];
@@ -162,10 +168,10 @@ tdl_sum_kernel(const float* __restrict__ tokens, const float* __restrict__ adden
     }
   };
   float4 tv[NV], av[NV], tn[NV], an[NV];
-  if (warp < N) load_row(warp, tv, av);
-  for (int p = warp; p < N; p += kTdlWarps) {
+  if (p_lo + warp < p_hi) load_row(p_lo + warp, tv, av);
+  for (int p = p_lo + warp; p < p_hi; p += kTdlWarps) {
     const int t = c * N + p;
-    if (p + kTdlWarps < N) load_row(p + kTdlWarps, tn, an);
+    if (p + kTdlWarps < p_hi) load_row(p + kTdlWarps, tn, an);
     float4 y[NV];
     float ss = 0.f;
 #pragma unroll
@@ -197,18 +203,59 @@ tdl_sum_kernel(const float* __restrict__ tokens, const float* __restrict__ adden
   }
   if (lane == 0) red[kTdlWarps * D + warp] = q;
   __syncthreads();
-  for (int col = threadIdx.x; col < D; col += blockDim.x) {
-    float t = 0.f;
+  if (split == 1) {
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+      float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < kTdlWarps; ++w) t += red[w * D + col];
-    S[static_cast<size_t>(bc) * D + col] = t;
+      for (int w = 0; w < kTdlWarps; ++w) t += red[w * D + col];
+      S[static_cast<size_t>(bc) * D + col] = t;
+    }
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kTdlWarps; ++w) t += red[kTdlWarps * D + w];
+      Q[bc] = t;
+    }
+    return;
+  }
+  // cluster path: every CTA folds its warps into row 0 of `red`, rank 0 then adds the peers' rows in rank order
+  float tcol[4];  // D <= 4 * blockDim.x
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int col = threadIdx.x + k * blockDim.x;
+    float t = 0.f;
+    if (col < D) {
+#pragma unroll
+      for (int w = 0; w < kTdlWarps; ++w) t += red[w * D + col];
+    }
+    tcol[k] = t;
+  }
+  __syncthreads();  // every warp row has been read before row 0 is overwritten
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int col = threadIdx.x + k * blockDim.x;
+    if (col < D) red[col] = tcol[k];
   }
   if (threadIdx.x == 0) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < kTdlWarps; ++w) t += red[kTdlWarps * D + w];
-    Q[bc] = t;
+    red[kTdlWarps * D] = t;
   }
+  cluster_sync_all();
+  if (rank == 0) {
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+      float t = red[col];
+      for (int rk = 1; rk < split; ++rk) t += ld_dsmem_f32(&red[col], rk);
+      S[static_cast<size_t>(bc) * D + col] = t;
+    }
+    if (threadIdx.x == 0) {
+      float t = red[kTdlWarps * D];
+      for (int rk = 1; rk < split; ++rk) t += ld_dsmem_f32(&red[kTdlWarps * D], rk);
+      Q[bc] = t;
+    }
+  }
+  cluster_sync_all();  // peers keep their shared memory alive until rank 0 has read it
 }
 
 // block-wide sum of one float per thread (blockDim.x <= 1024, multiple of 32)
@@ -743,8 +790,23 @@ int tdl_fwd(const float* tokens, const float* addend, const float* bias, float* 
   if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "tdl_fwd: D %% 4");
   ProfScope prof(PT_TDL, st);
   const size_t smem = (static_cast<size_t>(kTdlWarps) * D + kTdlWarps) * sizeof(float);
-  DCV_NV_SWITCH(D, tdl_sum_kernel<NV><<<B * Cs, kTdlWarps * 32, smem, st>>>(tokens, addend, bias, S, Q, rnorm, Cs, N, D));
-  DCV_CUDA(cudaGetLastError());
+  {
+    // token-sliced clusters when B*C' CTAs alone leave SMs idle (JUMP-CP: 32 x 8 = 256 CTAs for 148 SMs)
+    const int split = (B * Cs < 4 * num_sms() && N >= 64) ? 4 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * Cs * split);
+    cfg.blockDim = dim3(kTdlWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = split;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = split > 1 ? 1 : 0;
+    DCV_NV_SWITCH(D, DCV_CUDA(cudaLaunchKernelEx(&cfg, tdl_sum_kernel<NV>, tokens, addend, bias, S, Q, rnorm, Cs, N, D, split)));
+  }
   TdlFlags f{gamma_s, gamma_d, reverse_pos_pairs, use_square};
   tdl_pair_kernel<<<B, 128, 0, st>>>(S, Q, S_all, loss_b, coef_pos, coef_neg, B, Cs, N, D, f);
   DCV_CUDA(cudaGetLastError());
