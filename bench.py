@@ -272,7 +272,7 @@ def ours(args, wname):
     model.train()
     model.direct_grad = True  # gradients land in .grad as views of one flat buffer, no per-tensor autograd nodes
     if world > 1:
-        model.enable_data_parallel()
+        model.enable_data_parallel(overlap=os.environ.get("DCV_DP_OVERLAP", "1") != "0")
     from diverse_channel_vit_b200.optim import FusedAdamW
 
     opt = FusedAdamW(model, lr=4e-4, weight_decay=0.04)  # timm/torch AdamW semantics, one launch on the flat buffers
