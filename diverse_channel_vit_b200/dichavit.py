@@ -422,7 +422,8 @@ class DiChaViT(nn.Module):
 
         # engine state
         self._flat: Optional[torch.Tensor] = None      # fp32 master parameters
-        self._bflat: Optional[torch.Tensor] = None     # bf16 copy, refreshed every forward
+        self._bflat: Optional[torch.Tensor] = None     # bf16 operand copy of the parameters
+        self._bflat_version = -1                       # _flat._version the bf16 copy corresponds to (-1: stale)
         self._layout: List[tuple] = []                 # (param, offset, numel)
         self._groups: List[tuple] = []                 # (name, start, end) gradient buckets in backward order
         self._pos_maps: Dict[tuple, torch.Tensor] = {}
@@ -461,6 +462,21 @@ class DiChaViT(nn.Module):
         groups.append(("tail", tail))
         return groups
 
+    def _param_version(self) -> int:
+        """Sum of the autograd version counters of every parameter (+ the flat buffer's): changes whenever torch
+        writes a parameter in place."""
+        try:
+            v = self._flat._version
+            for p, _, _ in self._layout:
+                v += p._version
+        except RuntimeError:  # inference tensors carry no version counter: never trust the copy
+            return -1
+        return v
+
+    def mark_params_dirty(self) -> None:
+        """Force the next forward to rebuild the bf16 operand copy (needed after writes through `p.data`)."""
+        self._bflat_version = -1
+
     def _ensure_flat(self, device) -> None:
         ok = self._flat is not None and self._flat.device == device
         if ok:
@@ -488,6 +504,7 @@ class DiChaViT(nn.Module):
                 p.data = flat[o:o + n].view(p.shape)
         self._flat, self._layout, self._groups = flat, layout, bounds
         self._bflat = torch.empty(off, dtype=torch.bfloat16, device=device)
+        self._bflat_version = -1
         self._off = {id(p): o for p, o, _ in layout}
 
     def _fptr(self, p) -> int:
@@ -696,9 +713,15 @@ class DiChaViT(nn.Module):
         if key not in self._arena_bytes:
             self._arena_bytes[key] = self._plan(B, C_in, H, W, keep)["arena"].off
         arena_min = self._arena_bytes[key]
-        # fp32 master -> bf16 operand copy of every parameter (one launch)
-        check(lib.dcv_cast_f32_bf16(c_void_p(self._flat.data_ptr()), c_void_p(self._bflat.data_ptr()),
-                                    c_longlong(self._flat.numel()), st), "dcv_cast_f32_bf16")
+        # fp32 master -> bf16 operand copy of every parameter (one launch) -- skipped while the copy is current: the
+        # fused AdamW step writes it itself, and any torch-side in-place write to a parameter (optimizer,
+        # load_state_dict, init) bumps that parameter's version counter.  Writes through `.data` are invisible to
+        # the counters: call mark_params_dirty() after them.
+        ver = self._param_version()
+        if ver < 0 or self._bflat_version != ver:
+            check(lib.dcv_cast_f32_bf16(c_void_p(self._flat.data_ptr()), c_void_p(self._bflat.data_ptr()),
+                                        c_longlong(self._flat.numel()), st), "dcv_cast_f32_bf16")
+            self._bflat_version = ver
         arena = pl["arena"].alloc(dev, arena_min)
         base = arena.data_ptr()
         scal = torch.zeros(4, dtype=torch.float32, device=dev)  # tdl, cdl, extra

@@ -71,6 +71,7 @@ class FusedAdamW:
                                  c_void_p(self.exp_avg_sq.data_ptr()), c_void_p(m._bflat.data_ptr()), c_longlong(n),
                                  c_float(self.lr), c_float(self.betas[0]), c_float(self.betas[1]), c_float(self.eps),
                                  c_float(self.weight_decay), self.step_count, clip_ptr, st), "dcv_adamw_step")
+        m._bflat_version = m._param_version()  # the kernel refreshed the bf16 operand copy (no torch-side version bump)
 
 
 def cosine_lr(num_updates: int, base_lr: float, t_initial: int, lr_min: float = 0.0, warmup_t: int = 0,

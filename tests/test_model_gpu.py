@@ -271,6 +271,32 @@ def test_fused_adamw_matches_torch():
             assert rel_l2(pa, pb) < 1e-5, (clip, ka, rel_l2(pa, pb))
 
 
+def test_bf16_operand_copy_tracks_parameter_writes():
+    """The fp32 -> bf16 parameter cast is skipped while the copy is current (fused AdamW writes it itself); every
+    torch-side in-place write must trigger a rebuild."""
+    from diverse_channel_vit_b200.optim import FusedAdamW
+
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["tiny_jumpcp"]
+    m = build_cuda_model(oc, mapper, O.make_weights(oc, has_head, wseed))
+    x, y = make_inputs(oc, B, 8, oc.num_classes, iseed)
+    x, y = x.cuda(), y.cuda()
+    opt = FusedAdamW(m, lr=1e-2, weight_decay=0.05)
+    cuda_step(m, x, y, chunk, has_head, xlam)
+    opt.step()
+    m.eval()
+    with torch.no_grad():
+        a = m(x, chunk)           # uses the bf16 copy written by the AdamW kernel
+        b = m(x, chunk)           # cast skipped again
+        m.mark_params_dirty()
+        c = m(x, chunk)           # fresh cast of the fp32 master
+        assert torch.equal(a, b) and torch.equal(a, c)
+        m.classifer_head.weight.mul_(1.5)  # torch-side in-place write: version counter moves
+        d = m(x, chunk)
+        m.mark_params_dirty()
+        e = m(x, chunk)
+        assert torch.equal(d, e) and not torch.equal(a, d)
+
+
 def test_direct_grad_mode_equals_autograd_mode():
     """direct_grad=True writes .grad as views of the flat gradient buffer (no per-parameter autograd nodes); values
     and accumulation semantics must equal the default autograd route."""
