@@ -261,6 +261,13 @@ int dcv_ln_bwd(const void* dy, const float* x, const float* mean, const float* r
   return ln_bwd(dy, x, mean, rstd, gamma, dres, dx_bf16, dgamma, dbeta, dxsum, M, D, ST(stream));
 }
 
+int dcv_attn_bwd_fused(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
+                       void* dqkv, float* dbias_qkv, int delta_ready, int B, int L, int H, float scale, void* stream) {
+  if (!qkv || !o || !dO || !lse2 || !delta || !dq_acc || !dqkv)
+    return set_error(DCV_ERR_INVALID, "dcv_attn_bwd_fused: null pointer");
+  return attn_bwd(qkv, o, dO, lse2, delta, dq_acc, dqkv, B, L, H, scale, ST(stream), false, delta_ready != 0, dbias_qkv);
+}
+
 int dcv_colsum_bf16(const void* a, float* out, int M, int N, int lda, void* stream) {
   if (!a || !out) return set_error(DCV_ERR_INVALID, "dcv_colsum_bf16: null pointer");
   return colsum_bf16(a, out, M, N, lda, ST(stream));

@@ -57,6 +57,8 @@ struct AttnBwdParams {
   const float* lse2;   // [B,H,Lp]
   const float* delta;  // [B,H,Lp]
   __nv_bfloat16* dqkv; // [B,L,3D]
+  float* dbias;        // optional [3D]: column sums of dqkv (qkv bias gradient) are ADDED here (dK / dV parts by the
+                       // main kernel's epilogue, the dQ part by the finish kernel)
 };
 
 // smem: K,V | Q x3 stages | dO x2 stages | dS^T x2 buffers (each 2 chunks of [128 kv][64 q]) |
@@ -439,6 +441,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       uint32_t a[16];
       tmem_ld16(tsrc + lane_base + cg * 16, a);
       tmem_ld_wait();
+      if (p.dbias != nullptr) {
+        // column sums over the 32 key rows of this warp (rows beyond L hold exact zeros): transposing butterfly,
+        // 16 shuffles, after which lane l owns column 8*b4 + 4*b3 + 2*b2 + b1 of its bits; even lanes add it
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(a[i]) * mul;
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {
+          const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const float send = up ? x[i] : x[i + w];
+            const float keep = up ? x[i + w] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * w);
+          }
+        }
+        x[0] += __shfl_xor_sync(0xffffffffu, x[0], 1);
+        if ((lane & 1) == 0) {
+          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          atomicAdd(p.dbias + (which + 1) * p.D + h * kHd + cg * 16 + col, x[0]);
+        }
+      }
       if (kv_ok) {
         __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + kv0 + r) * (3 * p.D) + (which + 1) * p.D +
                              h * kHd + cg * 16;
@@ -518,27 +542,54 @@ __global__ void attn_bwd_prep_cls_kernel(const __nv_bfloat16* __restrict__ o, co
   for (int i = lane; i < 128; i += 32) dst[i] = (i == 0) ? acc : 0.f;
 }
 
-// scale * dq_acc fp32 [B,H,L,64] -> dqkv bf16 [B,L,3D] columns [h*64, h*64+64)
-__global__ void attn_bwd_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, int B,
-                                       int L, int H, float scale) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // one per 8 elements
-  const long long total = static_cast<long long>(B) * H * L * 8;
-  if (gid >= total) return;
-  const int c8 = static_cast<int>(gid & 7);
-  long long t = gid >> 3;
-  const int q = static_cast<int>(t % L);
-  t /= L;
-  const int hh = static_cast<int>(t % H);
-  const int bb = static_cast<int>(t / H);
-  const float4* src = reinterpret_cast<const float4*>(dq_acc) + gid * 2;
-  const float4 a = __ldg(src), c = __ldg(src + 1);
-  uint4 o;
-  o.x = pack_bf16(a.x * scale, a.y * scale);
-  o.y = pack_bf16(a.z * scale, a.w * scale);
-  o.z = pack_bf16(c.x * scale, c.y * scale);
-  o.w = pack_bf16(c.z * scale, c.w * scale);
+// scale * dq_acc fp32 [B,H,L,64] -> dqkv bf16 [B,L,3D] columns [h*64, h*64+64); optionally the column sums of the
+// result (the q third of the qkv bias gradient) are added to dbias[0, D).
+// One CTA per (128 query rows, b*H + h): thread = (row lane 0..31, 8-column group); 4 rows per thread.
+constexpr int kFinRows = 128;
+__global__ void __launch_bounds__(256)
+attn_bwd_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
+                       int B, int L, int H, float scale) {
+  __shared__ float part[8][kHd];
+  const int bh = blockIdx.x;
+  const int bb = bh / H, hh = bh - bb * H;
+  const int c8 = threadIdx.x & 7, rr = threadIdx.x >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = H * kHd;
-  *reinterpret_cast<uint4*>(dqkv + (static_cast<size_t>(bb) * L + q) * (3 * D) + hh * kHd + c8 * 8) = o;
+  float sacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int it = 0; it < kFinRows / 32; ++it) {
+    const int q = blockIdx.y * kFinRows + it * 32 + rr;
+    if (q < L) {
+      const float4* src = reinterpret_cast<const float4*>(dq_acc + (static_cast<size_t>(bh) * L + q) * kHd + c8 * 8);
+      const float4 a = __ldg(src), c = __ldg(src + 1);
+      const float v[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, c.x * scale, c.y * scale, c.z * scale, c.w * scale};
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]);
+      o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dqkv + (static_cast<size_t>(bb) * L + q) * (3 * D) + hh * kHd + c8 * 8) = o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sacc[i] += v[i];
+    }
+  }
+  if (dbias == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // the warp's 4 row lanes
+    sacc[i] += __shfl_xor_sync(0xffffffffu, sacc[i], 8);
+    sacc[i] += __shfl_xor_sync(0xffffffffu, sacc[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[warp][c8 * 8 + i] = sacc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < kHd) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+    atomicAdd(dbias + hh * kHd + threadIdx.x, t);
+  }
 }
 
 }  // namespace
@@ -550,7 +601,8 @@ int debug_attn_timeline(long long* buf) {
 }
 
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
-             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only, bool delta_ready) {
+             void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only, bool delta_ready,
+             float* dbias_qkv) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(DCV_ERR_INVALID, "attn_bwd: empty problem");
   const int D = H * kHd;
   const int Lp = (L + 127) / 128 * 128;
@@ -592,6 +644,7 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   p.sl2 = scale * 1.4426950408889634f;
   p.lse2 = lse2; p.delta = delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.dbias = dbias_qkv;
   dim3 grid((L + kTk - 1) / kTk, H, B);
   {
     ProfScope prof(PT_ATTN_BWD, st);
@@ -600,9 +653,8 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   }
   {
     ProfScope prof(PT_ATTN_BWD_FIN, st);
-    const long long total = static_cast<long long>(B) * H * L * 8;
-    attn_bwd_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, scale);
+    attn_bwd_finish_kernel<<<dim3(B * H, (L + kFinRows - 1) / kFinRows), 256, 0, st>>>(
+        dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias_qkv, B, L, H, scale);
     DCV_CUDA(cudaGetLastError());
   }
   count_launch(delta_ready ? 2 : 3);

@@ -81,11 +81,12 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
              int q_tiles = 0);
 // cls_only: dO is compact [B, D] (gradient of the CLS rows of o, every other row being zero); only query tile 0 is
 // visited, dK / dV / dQ are still produced for all rows
+// dbias_qkv: optional [3D] fp32, the column sums of dqkv (= qkv bias gradient) are ADDED to it
 // delta_ready: delta[b,h,q] = sum_d dO*O was already produced (epilogue of the projection dgrad GEMM, EPI_DELTA; pad
 // rows [L, Lp) zero); otherwise a prep kernel computes it here
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
              void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only = false,
-             bool delta_ready = false);
+             bool delta_ready = false, float* dbias_qkv = nullptr);
 
 int debug_attn_timeline(long long* buf);
 

@@ -58,10 +58,13 @@ int block_bwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts
   DCV_TRY(gemm_nt(dres_bf16, D, p.proj_w, D, M, D, D, EPI_DELTA, nullptr, ws.d_o, nullptr, nullptr, a.o, D, true, st, 0, 0,
                   nullptr, 0, ws.delta, d.L));
   DCV_TRY(gemm_tn(dres_bf16, D, a.o, D, M, D, D, g.proj_w, D, 1, 0, st));
-  DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st, false, true));
+  // the qkv bias gradient (column sums of dqkv) comes out of the attention-backward epilogues
+  float* fused_db = g.qkv_b;
+  DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st, false, true,
+                   fused_db));
   DCV_TRY(gemm_nt(ws.dqkv, 3 * D, p.qkv_w, D, M, D, 3 * D, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
   DCV_TRY(gemm_tn(ws.dqkv, 3 * D, a.u, D, M, 3 * D, D, g.qkv_w, D, 1, 0, st));
-  DCV_TRY(colsum_bf16(ws.dqkv, g.qkv_b, M, 3 * D, 3 * D, st));
+  if (!fused_db) DCV_TRY(colsum_bf16(ws.dqkv, g.qkv_b, M, 3 * D, 3 * D, st));
   DCV_TRY(ln_bwd(ws.dv, a.x_in, a.mean1, a.rstd1, p.ln1_w, dres, dres_bf16, g.ln1_w, g.ln1_b, dbias_prev, M, D, st));
   return 0;
 }
@@ -98,10 +101,12 @@ int block_bwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_
   // ---- attention branch: only the CLS rows of the projection input carry gradient ----
   DCV_TRY(gemm_nt(dres_c_bf16, D, p.proj_w, D, B, D, D, EPI_BIAS, nullptr, ws.d_o, nullptr, nullptr, nullptr, D, true, st));
   DCV_TRY(gemm_tn(dres_c_bf16, D, a.o, LD, B, D, D, g.proj_w, D, 1, 0, st));
-  DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st, true));
+  float* fused_db = g.qkv_b;
+  DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st, true, false,
+                   fused_db));
   DCV_TRY(gemm_nt(ws.dqkv, 3 * D, p.qkv_w, D, M, D, 3 * D, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
   DCV_TRY(gemm_tn(ws.dqkv, 3 * D, a.u, D, M, 3 * D, D, g.qkv_w, D, 1, 0, st));
-  DCV_TRY(colsum_bf16(ws.dqkv, g.qkv_b, M, 3 * D, 3 * D, st));
+  if (!fused_db) DCV_TRY(colsum_bf16(ws.dqkv, g.qkv_b, M, 3 * D, 3 * D, st));
   // gradient w.r.t. the block input through the residual path: zero except the CLS rows
   DCV_CUDA(cudaMemsetAsync(dres, 0, static_cast<size_t>(M) * D * sizeof(float), st));
   DCV_CUDA(cudaMemcpy2DAsync(dres, static_cast<size_t>(LD) * sizeof(float), dres_c, static_cast<size_t>(D) * sizeof(float),

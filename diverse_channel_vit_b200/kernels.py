@@ -104,8 +104,9 @@ def attn_fwd(qkv, B, L, H, scale=None, o=None, lse2=None):
     return o, lse2
 
 
-def attn_bwd(qkv, o, do, lse2, B, L, H, scale=None, dqkv=None, delta=None, dq_acc=None):
-    """-> dqkv bf16 [B*L, 3*H*64]."""
+def attn_bwd(qkv, o, do, lse2, B, L, H, scale=None, dqkv=None, delta=None, dq_acc=None, dbias=None, delta_ready=False):
+    """-> dqkv bf16 [B*L, 3*H*64].  dbias (fp32 [3*H*64]): the column sums of dqkv are added to it by the kernels;
+    delta_ready: `delta` already holds rowsum(dO*O) per head (gemm_nn_delta)."""
     for t, n in ((qkv, "qkv"), (o, "o"), (do, "do")):
         _req(t, torch.bfloat16, n)
         assert t.is_contiguous()
@@ -114,14 +115,19 @@ def attn_bwd(qkv, o, do, lse2, B, L, H, scale=None, dqkv=None, delta=None, dq_ac
     if dqkv is None:
         dqkv = torch.empty((B * L, 3 * D), device=dev, dtype=torch.bfloat16)
     if delta is None:
+        assert not delta_ready
         delta = torch.empty((B, H, lpad(L)), device=dev, dtype=torch.float32)
     if dq_acc is None:
         dq_acc = torch.empty((B, H, L, 64), device=dev, dtype=torch.float32)
     scale = 64 ** -0.5 if scale is None else scale
-    check(_lib.lib().dcv_attn_bwd(ptr(qkv), ptr(o), ptr(do), ptr(lse2), ptr(delta), ptr(dq_acc), ptr(dqkv), B, L, H,
-                                  ctypes.c_float(scale), stream_ptr()), "dcv_attn_bwd")
+    if dbias is None and not delta_ready:
+        check(_lib.lib().dcv_attn_bwd(ptr(qkv), ptr(o), ptr(do), ptr(lse2), ptr(delta), ptr(dq_acc), ptr(dqkv), B, L, H,
+                                      ctypes.c_float(scale), stream_ptr()), "dcv_attn_bwd")
+    else:
+        check(_lib.lib().dcv_attn_bwd_fused(ptr(qkv), ptr(o), ptr(do), ptr(lse2), ptr(delta), ptr(dq_acc), ptr(dqkv),
+                                            ptr(dbias), int(delta_ready), B, L, H, ctypes.c_float(scale), stream_ptr()),
+              "dcv_attn_bwd_fused")
     return dqkv
-
 
 def ln_fwd(x, gamma, beta, eps=1e-6):
     """x fp32 [M,D] -> (y bf16, mean, rstd)."""

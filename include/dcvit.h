@@ -86,6 +86,12 @@ int dcv_attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, flo
  * Replaces the autograd backward of models/vit.py:126-141. */
 int dcv_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
                  void* dqkv, int B, int L, int H, float scale, void* stream);
+/* Same, with the two fusions the block backward uses: delta_ready != 0 -> delta[b,h,q] was already produced by
+ * dcv_gemm_nn_delta (no prep pass); dbias_qkv != NULL (fp32 [3*H*64]) -> the column sums of dqkv,
+ * i.e. the qkv bias gradient (autograd of models/vit.py:121), are ADDED to it by the kernels' epilogues. */
+int dcv_attn_bwd_fused(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
+                       void* dqkv, float* dbias_qkv, int delta_ready, int B, int L, int H, float scale, void* stream);
+
 
 /* LayerNorm forward over rows (nn.LayerNorm, biased variance): x fp32 [M,D] -> y bf16 [M,D],
  * mean/rstd fp32 [M].  Replaces models/vit.py:384,398 (norm1, norm2; eps 1e-6 dichavit.py:724). */

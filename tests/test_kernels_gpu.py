@@ -59,6 +59,21 @@ def test_gemm_nn_dgrad(K, M, N, Kd):
     assert rel_l2(dg, hf.grad) < 1e-2
 
 
+@pytest.mark.parametrize("B,L,H", [(2, 197, 3), (3, 81, 6), (1, 1569, 6), (4, 33, 2)])
+def test_attn_bwd_fused_bias_gradient_and_delta(K, B, L, H):
+    """the block backward's fused path: delta from the projection-dgrad epilogue, qkv bias gradient from the
+    attention-backward epilogues == column sums of the dqkv the plain path stores"""
+    D = H * 64
+    qkv, dy, w = _bf(B * L, 3 * D, seed=21), _bf(B * L, D, seed=22), _bf(D, D, scale=0.05, seed=23)
+    o, lse = K.attn_fwd(qkv, B, L, H)
+    d_o, delta = K.gemm_nn_delta(dy, w, o, B, L)
+    ref = K.attn_bwd(qkv, o, d_o, lse, B, L, H)
+    dbias = torch.full((3 * D,), 0.25, device="cuda")  # accumulates on top of what is there
+    got = K.attn_bwd(qkv, o, d_o, lse, B, L, H, delta=delta, delta_ready=True, dbias=dbias)
+    assert rel_l2(got, ref) < 2e-3  # same kernels; dQ accumulation order (fp32 reductions) differs run to run
+    assert rel_l2(dbias - 0.25, got.float().sum(0)) < 5e-3  # fp32 sums before the bf16 rounding vs sums of rounded values
+
+
 @pytest.mark.parametrize("B,L,H", [(2, 197, 6), (3, 81, 3), (1, 1569, 6)])
 def test_gemm_nn_delta(K, B, L, H):
     """projection dgrad with the fused softmax-backward row term delta = rowsum_head(dO * O)"""
