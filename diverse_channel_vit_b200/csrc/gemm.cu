@@ -25,7 +25,7 @@ enum GemmEpilogue : int {
   EPI_BIAS = 0,        // out_bf16 = acc (+ bias)
   EPI_BIAS_GELU = 1,   // out_bf16 = h = acc + bias ; out2_bf16 = gelu(h)
   EPI_BIAS_RESID = 2,  // out_f32 = resid + acc + bias   (resid may alias out_f32)
-  EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux)
+  EPI_DGELU = 3,       // out_bf16 = acc * gelu'(aux)   (+ optional column sums of the result, see GemmNtParams::delta)
   EPI_F32 = 4,         // out_f32 = acc (+ bias)
   EPI_EMBED = 5,       // out_f32[(m / T) * L + 1 + m % T][:] = acc + addend[m % T][:]   (patch embedding)
   EPI_DELTA = 6,       // out_bf16 = dO = acc ; delta[b, h, q] = sum over head h's 64 columns of bf16(dO) * aux (aux = the
@@ -47,6 +47,7 @@ struct GemmNtParams {
   int map_T, map_L;
   const float* addend;
   // EPI_DELTA: rows m = (image b, query q) with q in [0, seq_L); delta fp32 [B, N/64, seq_Lp]
+  // EPI_DGELU: optional fp32 [N]: the column sums of the output (bias gradient of the layer below) are ADDED to it
   float* delta;
   int seq_L, seq_Lp;
 };
@@ -359,15 +360,35 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 8; ++j) {
             const float2 h0 = unpack_bf16(hr[4 * j]), h1 = unpack_bf16(hr[4 * j + 1]), h2 = unpack_bf16(hr[4 * j + 2]),
                          h3 = unpack_bf16(hr[4 * j + 3]);
-            st_shared_v4(s_out + sw128_offset(lane, j),
-                         pack_bf16(__uint_as_float(v[8 * j + 0]) * gelu_exact_grad(h0.x),
-                                   __uint_as_float(v[8 * j + 1]) * gelu_exact_grad(h0.y)),
-                         pack_bf16(__uint_as_float(v[8 * j + 2]) * gelu_exact_grad(h1.x),
-                                   __uint_as_float(v[8 * j + 3]) * gelu_exact_grad(h1.y)),
-                         pack_bf16(__uint_as_float(v[8 * j + 4]) * gelu_exact_grad(h2.x),
-                                   __uint_as_float(v[8 * j + 5]) * gelu_exact_grad(h2.y)),
-                         pack_bf16(__uint_as_float(v[8 * j + 6]) * gelu_exact_grad(h3.x),
-                                   __uint_as_float(v[8 * j + 7]) * gelu_exact_grad(h3.y)));
+            float y[8];
+            y[0] = __uint_as_float(v[8 * j + 0]) * gelu_exact_grad(h0.x);
+            y[1] = __uint_as_float(v[8 * j + 1]) * gelu_exact_grad(h0.y);
+            y[2] = __uint_as_float(v[8 * j + 2]) * gelu_exact_grad(h1.x);
+            y[3] = __uint_as_float(v[8 * j + 3]) * gelu_exact_grad(h1.y);
+            y[4] = __uint_as_float(v[8 * j + 4]) * gelu_exact_grad(h2.x);
+            y[5] = __uint_as_float(v[8 * j + 5]) * gelu_exact_grad(h2.y);
+            y[6] = __uint_as_float(v[8 * j + 6]) * gelu_exact_grad(h3.x);
+            y[7] = __uint_as_float(v[8 * j + 7]) * gelu_exact_grad(h3.y);
+            st_shared_v4(s_out + sw128_offset(lane, j), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]),
+                         pack_bf16(y[6], y[7]));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] = __float_as_uint(y[i]);
+          }
+          if (p.delta != nullptr) {
+            // column sums of this warp's 32 x 64 block of dH (= its share of the fc1 bias gradient): transposing
+            // butterfly, 62 shuffles, after which lane l owns columns 2l and 2l+1 (rows beyond M are exact zeros)
+#pragma unroll
+            for (int bit = 16, n = 32; bit >= 1; bit >>= 1, n >>= 1) {
+              const bool up = (lane & bit) != 0;
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+                const float send = __uint_as_float(up ? v[i] : v[i + n]);
+                const float keep = __uint_as_float(up ? v[i + n] : v[i]);
+                v[i] = __float_as_uint(keep + __shfl_xor_sync(0xffffffffu, send, bit));
+              }
+            }
+            atomicAdd(p.delta + col0 + 2 * lane, __uint_as_float(v[0]));
+            atomicAdd(p.delta + col0 + 2 * lane + 1, __uint_as_float(v[1]));
           }
         } else if (EPI == EPI_DELTA) {
           float dsum = 0.f;

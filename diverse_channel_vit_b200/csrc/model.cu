@@ -41,14 +41,15 @@ int block_bwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts
   const int M = d.B * d.L, D = d.D, F = d.F;
   // ---- MLP branch:  x_out = x_mid + fc2(gelu(fc1(LN2 x_mid))) ----
   // dh = (dres W2) o gelu'(h)            [M,F]
-  DCV_TRY(gemm_nt(dres_bf16, D, p.fc2_w, F, M, F, D, EPI_DGELU, nullptr, ws.dh, nullptr, nullptr, a.h, F, true, st));
+  // (the column sums of dh = fc1 bias gradient are accumulated by the same epilogue)
+  DCV_TRY(gemm_nt(dres_bf16, D, p.fc2_w, F, M, F, D, EPI_DGELU, nullptr, ws.dh, nullptr, nullptr, a.h, F, true, st, 0, 0,
+                  nullptr, 0, g.fc1_b));
   // dW2 += dres^T g                      [D,F]
   DCV_TRY(gemm_tn(dres_bf16, D, a.g, F, M, D, F, g.fc2_w, F, 1, 0, st));
   // dv = dh W1                           [M,D]
   DCV_TRY(gemm_nt(ws.dh, F, p.fc1_w, D, M, D, F, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
-  // dW1 += dh^T v ; db1 += colsum(dh)
+  // dW1 += dh^T v
   DCV_TRY(gemm_tn(ws.dh, F, a.v, D, M, F, D, g.fc1_w, D, 1, 0, st));
-  DCV_TRY(colsum_bf16(ws.dh, g.fc1_b, M, F, F, st));
   // dres += LN2'(dv); column sums of the result = d proj bias
   DCV_TRY(ln_bwd(ws.dv, a.x_mid, a.mean2, a.rstd2, p.ln2_w, dres, dres_bf16, g.ln2_w, g.ln2_b, g.proj_b, M, D, st));
   // ---- attention branch:  x_mid = x_in + proj(attn(qkv(LN1 x_in))) ----
@@ -92,11 +93,11 @@ int block_bwd_cls(const dcv_dims& d, const dcv_block_params& p, const dcv_block_
   DCV_TRY(check_dims(d));
   const int M = d.B * d.L, D = d.D, F = d.F, B = d.B, LD = d.L * d.D;
   // ---- MLP branch on the CLS rows ----
-  DCV_TRY(gemm_nt(dres_c_bf16, D, p.fc2_w, F, B, F, D, EPI_DGELU, nullptr, ws.dh, nullptr, nullptr, a.h, F, true, st));
+  DCV_TRY(gemm_nt(dres_c_bf16, D, p.fc2_w, F, B, F, D, EPI_DGELU, nullptr, ws.dh, nullptr, nullptr, a.h, F, true, st, 0, 0,
+                  nullptr, 0, g.fc1_b));
   DCV_TRY(gemm_tn(dres_c_bf16, D, a.g, F, B, D, F, g.fc2_w, F, 1, 0, st));
   DCV_TRY(gemm_nt(ws.dh, F, p.fc1_w, D, B, D, F, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
   DCV_TRY(gemm_tn(ws.dh, F, a.v, D, B, F, D, g.fc1_w, D, 1, 0, st));
-  DCV_TRY(colsum_bf16(ws.dh, g.fc1_b, B, F, F, st));
   DCV_TRY(ln_bwd(ws.dv, a.x_mid, a.mean2, a.rstd2, p.ln2_w, dres_c, dres_c_bf16, g.ln2_w, g.ln2_b, g.proj_b, B, D, st));
   // ---- attention branch: only the CLS rows of the projection input carry gradient ----
   DCV_TRY(gemm_nt(dres_c_bf16, D, p.proj_w, D, B, D, D, EPI_BIAS, nullptr, ws.d_o, nullptr, nullptr, nullptr, D, true, st));
