@@ -457,7 +457,7 @@ def ours(args, wname):
         Tc = Lc - 1
         by["ln_fwd"] += (2 * (depth - 1) + 1) * M * D * (4 + 2)
         by["ln_bwd"] += (2 * (depth - 1) + 1) * M * D * 16
-        by["colsum"] += (depth - 1) * M * F * 2 + depth * M * 3 * D * 2
+        by["colsum"] += nb * Tc * D * 2  # patch-embed bias gradient only: the block bias gradients come out of GEMM / attention epilogues
         by["attn_bwd_fin"] += depth * M * D * (4 + 2)
         by["im2col"] += nb * Tc * (w["patch"] ** 2) * (4 + 6)
         by["tdl"] += nb * Tc * D * 4
