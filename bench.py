@@ -290,6 +290,8 @@ def ours(args, wname):
 
     from oracle_free_losses import proxy_loss as _proxy_loss  # noqa: E402  (plain torch loss glue of the trainer)
 
+    PREFETCH_DCS = os.environ.get("DCV_PREFETCH_DCS", "1") != "0"
+
     def step(x, y):
         opt.zero_grad(set_to_none=True)
         if chunks:  # trainer.py:846-931: one forward/backward per chunk, one optimiser step
@@ -305,6 +307,8 @@ def ours(args, wname):
             loss = F.cross_entropy(out, y) + extra * 1.0  # trainer.py:986-995
             loss.backward()
         opt.step()
+        if not chunks and PREFETCH_DCS:
+            model.prefetch_dcs("train", x.shape[1])  # next step's channel draw, same RNG sequence, enqueued early
         return loss
 
     def barrier():
@@ -315,6 +319,7 @@ def ours(args, wname):
     def timed(nsteps, e2e: bool, seed: int):
         """returns max-over-ranks elapsed ms (CUDA events) and per-step host-visible losses"""
         random.seed(seed)  # DCS draws: identical on every rank and in every pass
+        model.feature_extractor.patch_embed._prefetched = None  # a draw prefetched by the previous pass is stale
         torch.manual_seed(seed + 2)
         torch.cuda.manual_seed_all(seed + 4)
         barrier()

@@ -228,6 +228,11 @@ class PatchEmbedPerChannel(nn.Module):
         positions of the kept channels inside x, and their global channel ids, both on `device`.
         RNG consumption is the reference's: random.randint(1,C), random.randint(0,C-1), then
         torch.multinomial on the device generator.  Nothing is copied back to the host."""
+        pre = getattr(self, "_prefetched", None)
+        if pre is not None:
+            self._prefetched = None
+            if pre[0] == (chunk_name, n_in, str(device), self.training, self.enable_sample):
+                return pre[1]
         chan = self.chunk_channels(chunk_name, device)
         if chan.numel() != n_in:
             raise ValueError(f"x has {n_in} channels but mapper['{chunk_name}'] lists {chan.numel()}")
@@ -262,6 +267,16 @@ class PatchEmbedPerChannel(nn.Module):
             self.counter.add(gid)
         return c_new, indices.to(torch.int32), gid.to(torch.int32)
 
+
+    def prefetch(self, chunk_name: str, n_in: int, device) -> None:
+        """Draw the NEXT forward's DCS selection now (same RNG calls, just earlier) so that the ~20 tiny sampling
+        launches overlap the GPU work still queued from the current step instead of sitting between the host's
+        per-step synchronisation and the first heavy kernel.  Opt-in: the next forward uses the draw iff it asks for
+        the same (chunk, channel count, device, mode); nothing else may consume the RNGs in between if bit-exact
+        agreement with an un-prefetched run is required."""
+        self._prefetched = None
+        key = (chunk_name, n_in, str(device), self.training, self.enable_sample)
+        self._prefetched = (key, self.select_channels(chunk_name, n_in, device))
 
     def leave_one_out_tokens(self, chunk_name: str, training_chunks: str, new_channel_init) -> Optional[torch.Tensor]:
         """Eval-time channel tokens for chunks with channels unseen in training (reference dichavit.py:219-374).
@@ -472,6 +487,10 @@ class DiChaViT(nn.Module):
         except RuntimeError:  # inference tensors carry no version counter: never trust the copy
             return -1
         return v
+
+    def prefetch_dcs(self, chunk_name: str, n_in: int) -> None:
+        """See PatchEmbedPerChannel.prefetch: overlap the next step's channel sampling with the current step."""
+        self.feature_extractor.patch_embed.prefetch(chunk_name, n_in, self._flat.device if self._flat is not None else "cuda")
 
     def mark_params_dirty(self) -> None:
         """Force the next forward to rebuild the bf16 operand copy (needed after writes through `p.data`)."""

@@ -297,6 +297,35 @@ def test_bf16_operand_copy_tracks_parameter_writes():
         assert torch.equal(d, e) and not torch.equal(a, d)
 
 
+def test_dcs_prefetch_draws_the_same_sequence():
+    """prefetch() only moves the RNG calls of the next forward earlier: the sequence of (C', indices) is unchanged."""
+    import random
+
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["tiny_jumpcp"]
+    oc = O.OracleConfig(**{**oc.__dict__, "enable_sample": True, "hcs_sampling": "lowest_cosine_prob", "hcs_sampling_temp": 0.1})
+    m = build_cuda_model(oc, mapper, O.make_weights(oc, has_head, wseed)).train()
+    pe = m.feature_extractor.patch_embed
+    n_in = len(mapper[chunk])
+
+    def draws(prefetch):
+        random.seed(11); torch.manual_seed(13); torch.cuda.manual_seed_all(17)
+        pe._prefetched = None
+        got = []
+        for _ in range(8):
+            cs, idx, gid = pe.select_channels(chunk, n_in, torch.device("cuda"))
+            got.append((cs, idx.cpu().tolist(), gid.cpu().tolist()))
+            if prefetch:
+                pe.prefetch(chunk, n_in, torch.device("cuda"))
+        return got
+
+    a, b = draws(False), draws(True)
+    assert a == b and len({d[0] for d in a}) > 1
+    pe.prefetch(chunk, n_in, torch.device("cuda"))
+    m.eval()  # a mode change invalidates the prefetched draw
+    cs, idx, gid = pe.select_channels(chunk, n_in, torch.device("cuda"))
+    assert cs == n_in and idx is None
+
+
 def test_direct_grad_mode_equals_autograd_mode():
     """direct_grad=True writes .grad as views of the flat gradient buffer (no per-parameter autograd nodes); values
     and accumulation semantics must equal the default autograd route."""
