@@ -307,8 +307,12 @@ def ours(args, wname):
             loss = F.cross_entropy(out, y) + extra * 1.0  # trainer.py:986-995
             loss.backward()
         opt.step()
-        if not chunks and PREFETCH_DCS:
-            model.prefetch_dcs("train", x.shape[1])  # next step's channel draw, same RNG sequence, enqueued early
+        if PREFETCH_DCS:  # next step's (first) channel draw: same RNG sequence, enqueued before the host reads the loss
+            if chunks:
+                first = next(iter(chunks))
+                model.prefetch_dcs(first, len(chunks[first][0]))
+            else:
+                model.prefetch_dcs("train", x.shape[1])
         return loss
 
     def barrier():
