@@ -829,7 +829,7 @@ int gemm_nt(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   int bn = 0;
   // 128 x 256 tiles for wide forward layers (fc1: 91 -> 84.5 us; operand traffic per MMA flop drops 10 %); the dgrad
   // flavour (MN-major B) measured no gain
-  if (!b_mn && N % 256 == 0 && N >= 1024 && epi != EPI_EMBED) bn = 256;
+  if (!b_mn && N % 256 == 0 && N >= 1024 && epi != EPI_EMBED && !g_nt_pair && g_nt_cluster == 1) bn = 256;
   else if (N % 192 == 0) bn = 192;
   else if (N % 128 == 0) bn = 128;
   else if (N % 64 == 0) bn = 64;
