@@ -136,3 +136,33 @@ def test_dcs_host_rng_consumption():
     st = random.getstate()
     assert pe.select_channels("HPA", 4, torch.device("cpu"))[1] is None
     assert random.getstate() == st
+
+
+def test_dcs_prefetch_keeps_the_draw_sequence_cpu():
+    """prefetch() moves the RNG calls of the next forward earlier; the sequence of draws is unchanged, a stale or
+    mismatching prefetch is dropped."""
+    oc, mapper, chunk, *_ = cases()["tiny_chammi_hpa"]
+    cfg = ref_cfg(oc)
+    cfg["enable_sample"] = True
+    cfg["hcs_sampling"] = "lowest_cosine_prob"
+    m = D.dichavit(cfg, mapper=mapper).train()
+    pe = m.feature_extractor.patch_embed
+    dev = torch.device("cpu")
+
+    def draws(prefetch):
+        random.seed(3)
+        torch.manual_seed(4)
+        pe._prefetched = None
+        out = []
+        for _ in range(10):
+            c, idx, gid = pe.select_channels("HPA", 4, dev)
+            out.append((c, idx.tolist(), gid.tolist()))
+            if prefetch:
+                pe.prefetch("HPA", 4, dev)
+        return out
+
+    assert draws(False) == draws(True)
+    pe.prefetch("HPA", 4, dev)
+    assert pe._prefetched is not None
+    m.eval()
+    assert pe.select_channels("HPA", 4, dev)[1] is None and pe._prefetched is None  # mode changed: dropped
