@@ -21,7 +21,7 @@ GRAD_TOL = 3e-2
 
 
 def _oracle(name, indices=None):
-    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()[name]
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = name if isinstance(name, tuple) else cases()[name]
     weights = O.make_weights(oc, has_head, wseed)
     x, y = make_inputs(oc, B, len(mapper[chunk]), oc.num_classes, iseed)
     loss, o, grads = O.loss_and_grads(x, y, weights, oc, mapper[chunk], has_head, indices=indices, extra_loss_lambda=xlam)
@@ -62,6 +62,15 @@ def _check_step(name, indices=None, golden=True):
 @pytest.mark.parametrize("name", [n for n in cases() if n.startswith("tiny")])
 def test_training_step_matches_oracle_and_reference_golden(name):
     _check_step(name)
+
+
+def test_training_step_vit_base():
+    """BASELINE.json configs[4] architecture (ViT-B: D=768, 12 heads) at a small image size, all losses on, full
+    channels: logits, losses and every parameter gradient against the oracle."""
+    oc = O.OracleConfig(pretrained_model_name="base", img_size=32, patch_size=8,
+                        in_channel_names=[f"c{i}" for i in range(8)], num_classes=10, proxy_loss_lambda=0.001,
+                        ortho_loss_v1_lambda=0.001, gamma_s=1.0, gamma_d=4.0, reverse_pos_pairs=True)
+    _check_step((oc, {"train": list(range(8))}, "train", True, 2, 51, 52, 1.0), golden=False)
 
 
 def test_training_step_vit_small_c1():
