@@ -288,7 +288,7 @@ def ours(args, wname):
     # > 126 MB L2 flush buffer, written between timed steps is unnecessary here: one step streams several GB
     # of activations (far larger than L2); stated in config.l2.
 
-    from oracle_free_losses import proxy_loss as _proxy_loss  # noqa: E402  (plain torch loss glue of the trainer)
+    from diverse_channel_vit_b200.trainer_glue import proxy_loss as _proxy_loss  # plain torch loss glue of the trainer
 
     PREFETCH_DCS = os.environ.get("DCV_PREFETCH_DCS", "1") != "0"
 

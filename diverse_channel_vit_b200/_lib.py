@@ -10,8 +10,12 @@ import re
 from ctypes import c_int, c_longlong, c_void_p, c_float, c_char_p
 from pathlib import Path
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libdcvit.so"
+# DCV_LIB=<variant> loads a validation build (libdcvit_<variant>.so, see build.py VARIANTS); default: the shipped library
+_VARIANT = os.environ.get("DCV_LIB", "")
+LIB_PATH = PKG_DIR / (f"libdcvit_{_VARIANT}.so" if _VARIANT else "libdcvit.so")
 HEADER_PATH = PKG_DIR.parent / "include" / "dcvit.h"
 
 

@@ -41,38 +41,46 @@ def _stale(target: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def _compile(src: Path, obj: Path) -> str:
-    cmd = [NVCC, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+def _compile(src: Path, obj: Path, extra=()) -> str:
+    cmd = [NVCC, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
     return r.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+# validation variants: extra -D flags, separate object directory and library name (libdcvit_<variant>.so)
+VARIANTS = {"erf": ["-DDCV_GELU_ERF"], "timeline": ["-DDCV_ATTN_TIMELINE"]}
+
+
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> Path:
+    build_dir = BUILD_DIR / variant if variant else BUILD_DIR
+    lib_path = PKG_DIR / f"libdcvit_{variant}.so" if variant else LIB_PATH
+    extra = VARIANTS[variant] if variant else []
+    build_dir.mkdir(parents=True, exist_ok=True)
     hdrs = _headers()
     jobs = []
     objs = []
     for src in _sources():
-        obj = BUILD_DIR / (src.stem + ".o")
+        obj = build_dir / (src.stem + ".o")
         objs.append(obj)
         if force or _stale(obj, [src, *hdrs]):
             jobs.append((src, obj))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-            logs = list(ex.map(lambda j: _compile(*j), jobs))
-        (BUILD_DIR / "ptxas.log").write_text("\n".join(logs))
+            logs = list(ex.map(lambda j: _compile(*j, extra), jobs))
+        (build_dir / "ptxas.log").write_text("\n".join(logs))
         if verbose:
             sys.stderr.write("\n".join(logs))
-    if force or jobs or _stale(LIB_PATH, objs):
-        cmd = [NVCC, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static"]
+    if force or jobs or _stale(lib_path, objs):
+        cmd = [NVCC, "-shared", "-o", str(lib_path), *map(str, objs), "-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var)
     print(p)

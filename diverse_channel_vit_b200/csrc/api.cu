@@ -55,14 +55,32 @@ ProfScope::~ProfScope() {
 }
 
 int num_sms() {
-  static int sms = 0;
+  static std::atomic<int> sms_by_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int sms = sms_by_dev[dev].load(std::memory_order_relaxed);
   if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    sms_by_dev[dev].store(sms, std::memory_order_relaxed);
   }
   return sms;
+}
+
+int ensure_smem_attr(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, uint64_t> done;  // kernel -> bit mask of devices that carry the attribute
+  int dev = 0;
+  DCV_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(kernel);
+    if (it != done.end() && (it->second & bit)) return 0;
+  }
+  DCV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  std::lock_guard<std::mutex> lk(mu);
+  done[kernel] |= bit;
+  return 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -284,6 +302,17 @@ int dcv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, l
   return adamw_step(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, clip, ST(stream));
 }
 
+int dcv_optim_sched_step(dcv_optim_state* state, const dcv_sched* cfg, void* stream) {
+  if (!state || !cfg) return set_error(DCV_ERR_INVALID, "dcv_optim_sched_step: null pointer");
+  return optim_sched_step(state, *cfg, ST(stream));
+}
+
+int dcv_adamw_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float beta1, float beta2,
+                       float eps, const dcv_optim_state* state, const float* clip, void* stream) {
+  if (!p || !g || !m || !v || !state) return set_error(DCV_ERR_INVALID, "dcv_adamw_step_dev: null pointer");
+  return adamw_step_dev(p, g, m, v, p_bf16, n, beta1, beta2, eps, state, clip, ST(stream));
+}
+
 int dcv_sumsq_f32(const float* g, long long n, float* out, void* stream) {
   if (!g || !out) return set_error(DCV_ERR_INVALID, "dcv_sumsq_f32: null pointer");
   return sumsq_f32(g, n, out, ST(stream));
@@ -353,6 +382,11 @@ void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo
 void dcv_debug_set_nt_cluster(int cm) { debug_set_nt_cluster(cm); }
 
 int dcv_debug_attn_timeline(long long* buf) { return debug_attn_timeline(buf); }
+
+void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode) {
+  if (fwd_mode >= 0) debug_set_attn_fwd_mode(fwd_mode);
+  if (bwd_mode >= 0) debug_set_attn_bwd_mode(bwd_mode);
+}
 
 int dcv_profile_num_tags(void) { return PT_COUNT; }
 const char* dcv_profile_tag_name(int tag) { return (tag >= 0 && tag < PT_COUNT) ? kProfNames[tag] : ""; }

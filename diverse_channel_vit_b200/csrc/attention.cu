@@ -41,6 +41,8 @@ __device__ long long* g_fwd_timeline = nullptr;
 #else
 #define TLF(role, it, pt) ((void)tl)
 #endif
+static int g_fwd_mode = 1;
+void debug_set_attn_fwd_mode(int m) { g_fwd_mode = m; }
 int debug_fwd_timeline(long long* buf) {
   DCV_CUDA(cudaMemcpyToSymbol(g_fwd_timeline, &buf, sizeof(buf)));
   return 0;
@@ -62,6 +64,11 @@ constexpr int kFwdSmem = kTq * kHd * 2 + kFwdStages * 2 * kTk * kHd * 2 + 1024 +
 //   MMA warp  : S_{j+1} = Q K_{j+1}^T is issued at s_consumed(j), i.e. it runs underneath the exponentials of
 //               tile j; PV_j at p_full(j).  K and V ride separate 2-stage rings: the K slot is free again as soon
 //               as S_j has completed, the V slot after PV_j.
+// PK: packed-pair fp32 math (FFMA2 / FADD2) and 3-input max in the softmax; PM: 8-bit mask over the pairs of every group
+// of 8 score pairs whose exponentials are evaluated on the FMA pipe (exp2_poly_f32x2) instead of the MUFU.
+// WA: one mbarrier arrival per softmax warp (elected lane after __syncwarp) instead of one per thread, and P goes to
+// TMEM in two halves so that the first tcgen05.st overlaps the second half of the exponentials.
+template <bool PK, int PM, bool WA>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -102,8 +109,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_consumed, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_consumed, WA ? 4 : 128);
+    mbar_init(p_full, WA ? 4 : 128);
     mbar_init(p_free, 1);
     fence_barrier_init();
   }
@@ -194,7 +201,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       tmem_ld32(tS + lane_base + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_consumed);  // S_{j+1} may overwrite tS
+      if constexpr (WA) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_consumed);
+      } else {
+        mbar_arrive(s_consumed);  // S_{j+1} may overwrite tS
+      }
       TLF(1, j, 2);
       if (tail) {
 #pragma unroll
@@ -202,12 +214,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
           if (kv0 + i >= p.L) sr[i] = 0xff800000u;  // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if constexpr (PK) {
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+        for (int i = 0; i < 128; i += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+        }
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.sl2;
       const bool grow = mx > m + 8.0f;  // first tile: m = -inf -> true
@@ -236,26 +258,66 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       }
       TLF(1, j, 3);
       // exponentials in place (S_{j+1} and PV_{j-1} run on the tensor pipe meanwhile)
-      float sum0 = 0.f, sum1 = 0.f;
+      if constexpr (PK) {
+        const uint64_t sl2x2 = pack_f32x2(p.sl2, p.sl2), negm = pack_f32x2(-m, -m);
+        uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = sum_a;
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.sl2, -m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.sl2, -m));
-        sum0 += p0;
-        sum1 += p1;
-        sr[i >> 1] = pack_bf16(p0, p1);
+        for (int i = 0; i < 64; ++i) {
+          const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sl2x2, negm);
+          uint64_t pr;
+          float p0, p1;
+          if ((PM >> (i & 7)) & 1) {
+            pr = exp2_poly_f32x2(x);
+            unpack_f32x2(pr, p0, p1);
+          } else {
+            unpack_f32x2(x, p0, p1);
+            p0 = fast_exp2(p0);
+            p1 = fast_exp2(p1);
+            pr = pack_f32x2(p0, p1);
+          }
+          if (i & 1) sum_b = add_f32x2(sum_b, pr); else sum_a = add_f32x2(sum_a, pr);
+          sr[i] = pack_bf16(p0, p1);
+          if (WA && i == 31) {  // first half of P (key columns 0..63) -> TMEM while the second half is computed
+            if (!pv_done) {
+              mbar_wait(p_free, (j - 1) & 1);
+              tc_fence_after();
+              pv_done = true;
+            }
+            tmem_st16(tP + lane_base, *reinterpret_cast<uint32_t(*)[16]>(&sr[0]));
+            tmem_st16(tP + lane_base + 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[16]));
+          }
+        }
+        float s0, s1;
+        unpack_f32x2(add_f32x2(sum_a, sum_b), s0, s1);
+        l += s0 + s1;
+      } else {
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.sl2, -m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.sl2, -m));
+          sum0 += p0;
+          sum1 += p1;
+          sr[i >> 1] = pack_bf16(p0, p1);
+        }
+        l += sum0 + sum1;
       }
-      l += sum0 + sum1;
       TLF(1, j, 4);
       if (!pv_done) {  // PV_{j-1} has finished reading P_{j-1}
         mbar_wait(p_free, (j - 1) & 1);
         tc_fence_after();
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st16(tP + lane_base + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[c * 16]));
+      for (int c = (WA && PK) ? 2 : 0; c < 4; ++c)
+        tmem_st16(tP + lane_base + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[c * 16]));
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      if constexpr (WA) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      } else {
+        mbar_arrive(p_full);
+      }
       TLF(1, j, 5);
     }
 
@@ -301,11 +363,19 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
   if (int e = make_tmap_bf16_3d(&map, qkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D * 2,
                                 (uint64_t)L * 3 * D * 2, kHd, kTq, 1))
     return e;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DCV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
-    attr_done = true;
+  using KernelFn = void (*)(const CUtensorMap, const AttnFwdParams);
+  KernelFn kern;
+  switch (g_fwd_mode) {
+    case 0: kern = attn_fwd_kernel<false, 0, false>; break;
+    case 1: kern = attn_fwd_kernel<true, 0, false>; break;
+    case 2: kern = attn_fwd_kernel<true, 0x88, false>; break;  // 2 of 8 pairs on the FMA pipe
+    case 3: kern = attn_fwd_kernel<true, 0xA4, false>; break;  // 3 of 8
+    case 4: kern = attn_fwd_kernel<true, 0xAA, false>; break;  // 4 of 8
+    case 5: kern = attn_fwd_kernel<true, 0, true>; break;
+    case 6: kern = attn_fwd_kernel<true, 0x88, true>; break;
+    default: kern = attn_fwd_kernel<true, 0xA4, true>; break;
   }
+  DCV_TRY_SMEM_ATTR(kern, kFwdSmem);
   AttnFwdParams p;
   p.B = B; p.L = L; p.H = H; p.D = D;
   p.Lp = (L + 127) / 128 * 128;
@@ -315,7 +385,7 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
   const int all_tiles = (L + kTq - 1) / kTq;
   dim3 grid(q_tiles > 0 && q_tiles < all_tiles ? q_tiles : all_tiles, H, B);
   ProfScope prof(PT_ATTN_FWD, st);
-  attn_fwd_kernel<<<grid, 192, kFwdSmem, st>>>(map, p);
+  kern<<<grid, 192, kFwdSmem, st>>>(map, p);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

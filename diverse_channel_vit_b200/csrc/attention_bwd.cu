@@ -91,7 +91,9 @@ struct BwdBars {
 //   B part (tile i-1): dS^T = P^T o (dP^T - delta[q]), P^T kept packed in registers -> bf16 into the swizzled smem tile
 // The B part's FMA-pipe work fills the issue slots the A part leaves while it waits on the MUFU; four compute warps
 // per SM sub-partition hide the dependent-instruction latency.
-template <bool HAS_A, bool HAS_B>
+// PK: packed-pair fp32 math (FFMA2 / FADD2 / FMUL2); PM: 8-bit mask over every group of 8 score pairs whose exponentials
+// run on the FMA pipe (exp2_poly_f32x2) instead of the MUFU.
+template <bool HAS_A, bool HAS_B, bool PK, int PM>
 __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_base, BwdBars* bars, uint8_t* sStat,
                                           uint8_t* sdS, uint32_t tS, uint32_t tdP, uint32_t tP, float sl2, bool zero_row,
                                           uint32_t (&pkeep)[16], long long* tl) {
@@ -126,10 +128,30 @@ __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_ba
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 l4 = ld_shared_f4(s_lse + (16 * c + 4 * q) * 4);
-        s[16 * c + 4 * q + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 0]), sl2, -l4.x)));
-        s[16 * c + 4 * q + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 1]), sl2, -l4.y)));
-        s[16 * c + 4 * q + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 2]), sl2, -l4.z)));
-        s[16 * c + 4 * q + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 3]), sl2, -l4.w)));
+        if constexpr (PK) {
+          const uint64_t sl2x2 = pack_f32x2(sl2, sl2);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int e = 16 * c + 4 * q + 2 * hh;
+            const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), sl2x2,
+                                         hh ? pack_f32x2(-l4.z, -l4.w) : pack_f32x2(-l4.x, -l4.y));
+            float p0, p1;
+            if ((PM >> ((e >> 1) & 7)) & 1) {
+              unpack_f32x2(exp2_poly_f32x2(x), p0, p1);
+            } else {
+              unpack_f32x2(x, p0, p1);
+              p0 = fast_exp2(p0);
+              p1 = fast_exp2(p1);
+            }
+            s[e] = __float_as_uint(p0);
+            s[e + 1] = __float_as_uint(p1);
+          }
+        } else {
+          s[16 * c + 4 * q + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 0]), sl2, -l4.x)));
+          s[16 * c + 4 * q + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 1]), sl2, -l4.y)));
+          s[16 * c + 4 * q + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 2]), sl2, -l4.z)));
+          s[16 * c + 4 * q + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[16 * c + 4 * q + 3]), sl2, -l4.w)));
+        }
       }
     }
     if (HAS_B) {
@@ -143,14 +165,30 @@ __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_ba
         const float4 da = ld_shared_f4(s_del + (16 * c + 8 * v) * 4), db = ld_shared_f4(s_del + (16 * c + 8 * v + 4) * 4);
         const float2 p0 = unpack_bf16(pkeep[8 * c + 4 * v + 0]), p1 = unpack_bf16(pkeep[8 * c + 4 * v + 1]);
         const float2 p2 = unpack_bf16(pkeep[8 * c + 4 * v + 2]), p3 = unpack_bf16(pkeep[8 * c + 4 * v + 3]);
-        const float e0 = p0.x * (__uint_as_float(d[8 * v + 0]) - da.x);
-        const float e1 = p0.y * (__uint_as_float(d[8 * v + 1]) - da.y);
-        const float e2 = p1.x * (__uint_as_float(d[8 * v + 2]) - da.z);
-        const float e3 = p1.y * (__uint_as_float(d[8 * v + 3]) - da.w);
-        const float e4 = p2.x * (__uint_as_float(d[8 * v + 4]) - db.x);
-        const float e5 = p2.y * (__uint_as_float(d[8 * v + 5]) - db.y);
-        const float e6 = p3.x * (__uint_as_float(d[8 * v + 6]) - db.z);
-        const float e7 = p3.y * (__uint_as_float(d[8 * v + 7]) - db.w);
+        float e0, e1, e2, e3, e4, e5, e6, e7;
+        if constexpr (PK) {
+          unpack_f32x2(mul_f32x2(pack_f32x2(p0.x, p0.y),
+                                 sub_f32x2(pack_f32x2(__uint_as_float(d[8 * v + 0]), __uint_as_float(d[8 * v + 1])),
+                                           pack_f32x2(da.x, da.y))), e0, e1);
+          unpack_f32x2(mul_f32x2(pack_f32x2(p1.x, p1.y),
+                                 sub_f32x2(pack_f32x2(__uint_as_float(d[8 * v + 2]), __uint_as_float(d[8 * v + 3])),
+                                           pack_f32x2(da.z, da.w))), e2, e3);
+          unpack_f32x2(mul_f32x2(pack_f32x2(p2.x, p2.y),
+                                 sub_f32x2(pack_f32x2(__uint_as_float(d[8 * v + 4]), __uint_as_float(d[8 * v + 5])),
+                                           pack_f32x2(db.x, db.y))), e4, e5);
+          unpack_f32x2(mul_f32x2(pack_f32x2(p3.x, p3.y),
+                                 sub_f32x2(pack_f32x2(__uint_as_float(d[8 * v + 6]), __uint_as_float(d[8 * v + 7])),
+                                           pack_f32x2(db.z, db.w))), e6, e7);
+        } else {
+          e0 = p0.x * (__uint_as_float(d[8 * v + 0]) - da.x);
+          e1 = p0.y * (__uint_as_float(d[8 * v + 1]) - da.y);
+          e2 = p1.x * (__uint_as_float(d[8 * v + 2]) - da.z);
+          e3 = p1.y * (__uint_as_float(d[8 * v + 3]) - da.w);
+          e4 = p2.x * (__uint_as_float(d[8 * v + 4]) - db.x);
+          e5 = p2.y * (__uint_as_float(d[8 * v + 5]) - db.y);
+          e6 = p3.x * (__uint_as_float(d[8 * v + 6]) - db.z);
+          e7 = p3.y * (__uint_as_float(d[8 * v + 7]) - db.w);
+        }
         st_shared_v4(sdS_g + sw128_offset(r, 4 * (cg & 1) + 2 * c + v), pack_bf16(e0, e1), pack_bf16(e2, e3),
                      pack_bf16(e4, e5), pack_bf16(e6, e7));
       }
@@ -178,6 +216,7 @@ __device__ __forceinline__ void bwd_phase(int i, int cg, int r, uint32_t lane_ba
   TL(1 + cg, i, 4);
 }
 
+template <bool PK, int PM>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_dq, const AttnBwdParams p) {
@@ -426,10 +465,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_arrive(&bars->kv_tmem);
     }
     uint32_t pkeep[16];  // P^T of the previous tile, packed bf16 (B part of the next phase)
-    bwd_phase<true, false>(0, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
+    bwd_phase<true, false, PK, PM>(0, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
     for (int i = 1; i < n_q; ++i)
-      bwd_phase<true, true>(i, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
-    bwd_phase<false, true>(n_q, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
+      bwd_phase<true, true, PK, PM>(i, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
+    bwd_phase<false, true, PK, PM>(n_q, cg, r, lane_base, bars, sStat, sdS, tS, tdP, tP, p.sl2, !kv_ok, pkeep, tl);
 
     // ---- epilogue: dK (x scale) and dV rows of this key tile; column group cg writes d columns [16cg, 16cg+16) ----
     mbar_wait(&bars->dkv_full, 0);
@@ -594,6 +633,8 @@ attn_bwd_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restri
 
 }  // namespace
 
+static int g_bwd_mode = 1;
+void debug_set_attn_bwd_mode(int m) { g_bwd_mode = m; }
 int debug_fwd_timeline(long long* buf);  // attention.cu
 int debug_attn_timeline(long long* buf) {
   DCV_CUDA(cudaMemcpyToSymbol(g_attn_timeline, &buf, sizeof(buf)));
@@ -617,11 +658,15 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
     return e;
   if (int e = make_tmap_f32_3d(&map_dq, dq_acc, 64, (uint64_t)L, (uint64_t)B * H, 64 * 4, (uint64_t)L * 64 * 4, 32, kTq, 1))
     return e;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DCV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-    attr_done = true;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnBwdParams);
+  KernelFn kern;
+  switch (g_bwd_mode) {
+    case 0: kern = attn_bwd_kernel<false, 0>; break;
+    case 1: kern = attn_bwd_kernel<true, 0>; break;
+    case 2: kern = attn_bwd_kernel<true, 0x80>; break;  // 1 of 8 pairs on the FMA pipe
+    default: kern = attn_bwd_kernel<true, 0x88>; break; // 2 of 8
   }
+  DCV_TRY_SMEM_ATTR(kern, kBwdSmem);
   {
     ProfScope prof(PT_ATTN_BWD_PREP, st);
     if (delta_ready) {
@@ -648,7 +693,7 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   dim3 grid((L + kTk - 1) / kTk, H, B);
   {
     ProfScope prof(PT_ATTN_BWD, st);
-    attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(map_qkv, map_do, map_dq, p);
+    kern<<<grid, kBwdThreads, kBwdSmem, st>>>(map_qkv, map_do, map_dq, p);
     DCV_CUDA(cudaGetLastError());
   }
   {

@@ -850,11 +850,8 @@ int cdl_fwd(const float* chan_embed, const float* proxies, const int* gid, float
   if (Cs <= 0 || Cs > kCdlMaxC) return set_error(DCV_ERR_UNSUPPORTED, "cdl_fwd: C'=%d must be in [1,%d]", Cs, kCdlMaxC);
   ProfScope prof(PT_CDL, st);
   const size_t smem = static_cast<size_t>(2) * Cs * D * sizeof(float);
-  static bool attr_done = false;  // static + dynamic shared memory crosses the 48 KB default from C' = 14 (D = 384) on
-  if (!attr_done) {
-    DCV_CUDA(cudaFuncSetAttribute(cdl_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  // static + dynamic shared memory crosses the 48 KB default from C' = 14 (D = 384) on
+  DCV_TRY_SMEM_ATTR(cdl_fwd_kernel, 200 * 1024);
   if (smem > 200 * 1024) return set_error(DCV_ERR_UNSUPPORTED, "cdl_fwd: C'*D too large for one CTA");
   cdl_fwd_kernel<<<1, 256, smem, st>>>(chan_embed, proxies, gid, scale, loss, dE, dP, Cs, D);
   DCV_CUDA(cudaGetLastError());

@@ -755,11 +755,7 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
       if (int e = make_tmap_2d(&em.in, p.aux, false, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldin * 2, ET::kCW, 32))
         return e;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    DCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  DCV_TRY_SMEM_ATTR(kern, Cfg::kSmemBytes);
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int num_ct = ((m_tiles + CM - 1) / CM) * (p.N / BN);
   const int max_clusters = num_sms() / CM;
@@ -893,11 +889,7 @@ template <int BN>
 static int launch_tn(const CUtensorMap& ma, const CUtensorMap& mb, GemmTnParams p, cudaStream_t st) {
   using Cfg = TnCfg<BN>;
   auto kern = gemm_tn_kernel<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  DCV_TRY_SMEM_ATTR(kern, Cfg::kSmemBytes);
   const int tiles = ((p.Nout + kBM - 1) / kBM) * (p.Kout / BN);
   const int total_mb = (p.M + kBK - 1) / kBK;
   int splits = p.splits;

@@ -57,6 +57,14 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t inner, u
 int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (kernel, device): applied once for each pair, thread-safe
+int ensure_smem_attr(const void* kernel, int bytes);
+#define DCV_TRY_SMEM_ATTR(kern, bytes)                                            \
+  do {                                                                            \
+    int _rc = ::dcv::ensure_smem_attr(reinterpret_cast<const void*>(kern), bytes); \
+    if (_rc != 0) return _rc;                                                     \
+  } while (0)
+
 #define DCV_CUDA(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
@@ -89,6 +97,8 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
              bool delta_ready = false, float* dbias_qkv = nullptr);
 
 int debug_attn_timeline(long long* buf);
+void debug_set_attn_fwd_mode(int m);
+void debug_set_attn_bwd_mode(int m);
 
 // ---- rowops.cu ----
 int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D,
@@ -101,6 +111,9 @@ int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t st);
 int adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
                float beta2, float eps, float wd, int step, const float* clip, cudaStream_t st);
 int sumsq_f32(const float* g, long long n, float* out, cudaStream_t st);
+int adamw_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float beta1, float beta2,
+                   float eps, const dcv_optim_state* state, const float* clip, cudaStream_t st);
+int optim_sched_step(dcv_optim_state* state, const dcv_sched& cfg, cudaStream_t st);
 
 // ---- embed.cu ----
 int im2col_gather(const void* x, int x_is_u8, const float* pix_mean, const float* pix_inv_std, const int* idx,

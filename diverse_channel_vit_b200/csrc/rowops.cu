@@ -311,6 +311,88 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// Same update with every per-step scalar read from DEVICE memory (dcv_optim_state), so that a captured CUDA graph of
+// the optimiser step replays with the learning rate / weight decay / bias corrections of the current update.
+__global__ void __launch_bounds__(256)
+adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 __nv_bfloat16* __restrict__ p_bf16, long long n4, float beta1, float beta2, float eps,
+                 const dcv_optim_state* __restrict__ state, const float* __restrict__ clip) {
+  float gs = 1.0f;
+  if (clip != nullptr) {
+    const float norm = sqrtf(clip[0]);
+    gs = fminf(1.0f, clip[1] / (norm + 1e-6f));
+  }
+  const float lr = state->lr, wd = state->wd, bc2_sqrt = state->bc2_sqrt;
+  const float step_size = lr / state->bc1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = reinterpret_cast<float*>(&pv);
+    const float* gp = reinterpret_cast<const float*>(&gv);
+    float* mp = reinterpret_cast<float*>(&mv);
+    float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = gp[k] * gs;
+      pp[k] *= 1.0f - lr * wd;
+      mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
+      vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
+      const float denom = sqrtf(vp[k]) / bc2_sqrt + eps;
+      pp[k] -= step_size * (mp[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (p_bf16 != nullptr) {
+      uint2 o;
+      o.x = pack_bf16(pp[0], pp[1]);
+      o.y = pack_bf16(pp[2], pp[3]);
+      reinterpret_cast<uint2*>(p_bf16)[i] = o;
+    }
+  }
+}
+
+// One thread: advance the update counter and evaluate the schedules for the update about to be applied.
+//   lr  : timm CosineLRScheduler._get_lr(t) (reference lr_schedulers.py:6-9), t = u - 1 when the schedule counts
+//         updates (trainer.py:1009-1010 sets the next update's lr right after optimizer.step()) or the 1-based epoch
+//         number 1 + (u - 1) / updates_per_epoch when it counts epochs (trainer.py:344-348)
+//   wd  : utils.cosine_scheduler table (utils.py:563-574) indexed as trainer.py:1011-1019 does: update 1 runs with the
+//         optimiser's own weight decay (= table[0]), update u >= 2 with table[min(u - 2, len - 1)]
+__global__ void optim_sched_kernel(dcv_optim_state* st, dcv_sched c) {
+  const int u = st->num_updates + 1;
+  st->num_updates = u;
+  const int t = c.updates_per_epoch > 0 ? 1 + (u - 1) / c.updates_per_epoch : u - 1;
+  float lr = c.base_lr;
+  if (c.t_initial > 0) {
+    if (t < c.warmup_t) {
+      lr = c.warmup_lr_init + t * ((c.base_lr - c.warmup_lr_init) / c.warmup_t);
+    } else {
+      const int tt = c.warmup_prefix ? t - c.warmup_t : t;
+      const int i = tt / c.t_initial;
+      const int t_curr = tt - c.t_initial * i;
+      const double lr_max = static_cast<double>(c.base_lr) * pow(static_cast<double>(c.cycle_decay), static_cast<double>(i));
+      if (i < c.cycle_limit)
+        lr = static_cast<float>(c.lr_min + 0.5 * (lr_max - c.lr_min) *
+                                (1.0 + cos(3.14159265358979323846 * pow(static_cast<double>(t_curr), static_cast<double>(c.k_decay)) /
+                                           pow(static_cast<double>(c.t_initial), static_cast<double>(c.k_decay)))));
+      else
+        lr = c.lr_min;
+    }
+  }
+  float wd = c.wd_base;
+  if (c.wd_total > 0 && u >= 2) {
+    const int idx = min(u - 2, c.wd_total - 1);
+    wd = static_cast<float>(c.wd_end + 0.5 * (static_cast<double>(c.wd_base) - c.wd_end) *
+                            (1.0 + cos(3.14159265358979323846 * idx / static_cast<double>(c.wd_total))));
+  }
+  st->lr = lr;
+  st->wd = wd;
+  st->bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.beta1), static_cast<double>(u)));
+  st->bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(c.beta2), static_cast<double>(u))));
+}
+
 // out[0] += sum(g^2)   (global gradient norm for clipping; out zeroed by the caller)
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {
   __shared__ float red[8];
@@ -415,6 +497,27 @@ int adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long 
   const long long n4 = n >> 2;
   const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, static_cast<long long>(num_sms()) * 16));
   adamw_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n4, a, clip);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int adamw_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float beta1, float beta2,
+                   float eps, const dcv_optim_state* state, const float* clip, cudaStream_t st) {
+  if (n <= 0 || (n & 3)) return set_error(DCV_ERR_INVALID, "adamw_step_dev: n must be a positive multiple of 4");
+  ProfScope prof(PT_CAST, st);
+  const long long n4 = n >> 2;
+  const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, static_cast<long long>(num_sms()) * 16));
+  adamw_dev_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n4, beta1, beta2, eps,
+                                           state, clip);
+  DCV_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int optim_sched_step(dcv_optim_state* state, const dcv_sched& cfg, cudaStream_t st) {
+  if (cfg.t_initial > 0 && cfg.warmup_t < 0) return set_error(DCV_ERR_INVALID, "optim_sched_step: warmup_t < 0");
+  optim_sched_kernel<<<1, 1, 0, st>>>(state, cfg);
   DCV_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -446,12 +446,13 @@ class DiChaViT(nn.Module):
         self._pg = None
         self._comm_stream = None
         self.last_losses: Dict[str, torch.Tensor] = {}
-        self._x_is_u8 = False
-        self._pix_norm = None
         self._plan_cache: Dict[tuple, dict] = {}
         self._bp_cache = None
         self.direct_grad = False  # see _DiChaViTFn.backward
+        self.grad_sync = True     # data parallel: all-reduce in this backward (False inside no_sync())
         self._grad_anchor: Optional[torch.Tensor] = None
+        self._last_gflat: Optional[torch.Tensor] = None
+        self._dp_synced_ptr = 0   # data_ptr of the flat buffer whose contents were broadcast from rank 0
         self._arena_bytes: Dict[tuple, int] = {}   # forward arena size of the full-channel plan per input shape
         self._ws_bytes: Dict[tuple, int] = {}      # backward workspace high-water mark per input shape
 
@@ -476,6 +477,33 @@ class DiChaViT(nn.Module):
             tail.append(self.logit_scale)
         groups.append(("tail", tail))
         return groups
+
+    @property
+    def _external_ids(self):
+        """Parameters the module owns for the trainer but never reads in forward (`proxies`, `logit_scale`: used by the
+        trainer's loss glue, trainer.py:876-914).  Their gradients come from torch autograd, not from the kernels."""
+        ids = {id(self.proxies)}
+        if hasattr(self, "logit_scale"):
+            ids.add(id(self.logit_scale))
+        return ids
+
+    # engine caches hold raw device pointers (ctypes structs) and buffers tied to this instance: copies / pickles
+    # (AveragedModel for SWA at trainer.py:243, checkpointing of the module object) rebuild them lazily
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.update(_flat=None, _bflat=None, _bflat_version=-1, _layout=[], _groups=[], _pos_maps={}, _plan_cache={},
+                  _bp_cache=None, _grad_anchor=None, _last_gflat=None, _comm_stream=None, _pg=None, _arena_bytes={},
+                  _ws_bytes={}, last_losses={}, _dp_synced_ptr=0, _off={})
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)  # Parameter.__deepcopy__ clones: no view of our flat buffer survives
+        return new
 
     def _param_version(self) -> int:
         """Sum of the autograd version counters of every parameter (+ the flat buffer's): changes whenever torch
@@ -525,6 +553,53 @@ class DiChaViT(nn.Module):
         self._bflat = torch.empty(off, dtype=torch.bfloat16, device=device)
         self._bflat_version = -1
         self._off = {id(p): o for p, o, _ in layout}
+        self._last_gflat = None
+        self._sync_params_from_rank0()
+
+    def _sync_params_from_rank0(self) -> None:
+        """DDP broadcasts rank 0's parameters at construction (trainer.py:1185); the reference seeds every process
+        differently by default (trainer.py:81), so without this the replicas would start -- and stay -- different."""
+        if not self.grad_allreduce or self._flat is None or self._dp_synced_ptr == self._flat.data_ptr():
+            return
+        import torch.distributed as dist
+
+        dist.broadcast(self._flat, src=dist.get_global_rank(self._pg, 0) if self._pg is not None else 0, group=self._pg)
+        self._dp_synced_ptr = self._flat.data_ptr()
+        self._bflat_version = -1
+
+    def _allreduce_external(self, flat_slice: torch.Tensor) -> None:
+        """average a trainer-owned parameter's gradient (already copied into the flat buffer) over the ranks"""
+        import torch.distributed as dist
+
+        flat_slice.mul_(1.0 / dist.get_world_size(group=self._pg))
+        dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self._pg)
+
+    def allreduce_external_grads(self) -> None:
+        """Data parallel with a torch optimizer instead of FusedAdamW: the kernels' gradients are averaged by the
+        bucketed reducer during backward, those of `proxies` / `logit_scale` (produced by torch autograd from the
+        trainer's proxy loss) are averaged here -- call it after the last backward of the step."""
+        if not self.grad_allreduce:
+            return
+        for p in (self.proxies, getattr(self, "logit_scale", None)):
+            if p is not None and p.grad is not None:
+                self._allreduce_external(p.grad)
+
+    def no_sync(self):
+        """Context manager like DDP.no_sync(): backwards inside it do not all-reduce (gradient accumulation over
+        several forward/backward passes, e.g. the three CHAMMI chunks of one optimiser step, trainer.py:846-931);
+        the first backward outside it reduces the accumulated flat gradient."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old = self.grad_sync
+            self.grad_sync = False
+            try:
+                yield
+            finally:
+                self.grad_sync = old
+
+        return ctx()
 
     def _fptr(self, p) -> int:
         return self._flat.data_ptr() + 4 * self._off[id(p)]
@@ -554,6 +629,8 @@ class DiChaViT(nn.Module):
         self.grad_allreduce = True
         self._pg = process_group
         self._overlap = overlap
+        self._dp_synced_ptr = 0
+        self._sync_params_from_rank0()  # if the flat buffer exists already; else at its creation
         return self
 
     # ------------------------------------------------------------------ forward
@@ -565,34 +642,38 @@ class DiChaViT(nn.Module):
             raise ValueError("x must be [B, C, H, W]")
         # uint8 input: the loader's per-channel standardisation runs inside the patch-gather kernel (8(f) #3);
         # kwargs pixel_mean / pixel_std: [C] tensors or sequences in the order of x's channels
-        self._x_is_u8 = x.dtype == torch.uint8
-        self._pix_norm = None
-        if self._x_is_u8:
+        x_is_u8 = x.dtype == torch.uint8
+        pix_norm = None
+        if x_is_u8:
             x = x.contiguous()
             if kwargs.get("pixel_mean") is not None:
                 mean = torch.as_tensor(kwargs["pixel_mean"], dtype=torch.float32, device=x.device).contiguous()
                 std = torch.as_tensor(kwargs["pixel_std"], dtype=torch.float32, device=x.device).contiguous()
                 if mean.numel() != x.shape[1] or std.numel() != x.shape[1]:
                     raise ValueError("pixel_mean / pixel_std must have one entry per input channel")
-                self._pix_norm = (mean, (1.0 / std).contiguous())
+                pix_norm = (mean, (1.0 / std).contiguous())
         else:
             x = x.contiguous().float()
         self._ensure_flat(x.device)
         pe = self.feature_extractor.patch_embed
         cs, idx, gid = pe.select_channels(chunk_name, x.shape[1], x.device)
-        self._ce_override = None
+        ce_override = None
         if (not self.training) and training_chunks is not None:  # reference dichavit.py:219
-            self._ce_override = pe.leave_one_out_tokens(chunk_name, training_chunks, new_channel_init)
-            if self._ce_override is not None:
+            ce_override = pe.leave_one_out_tokens(chunk_name, training_chunks, new_channel_init)
+            if ce_override is not None:
                 gid = torch.arange(cs, dtype=torch.int32, device=x.device)  # rows of the synthesised token matrix
+        # everything the backward needs to know about THIS call travels with the autograd node, not on the module:
+        # a second forward, or a train()/eval() toggle, before backward() must not change the gradients
+        call = dict(training=self.training, x_is_u8=x_is_u8, pix_norm=pix_norm, ce_override=ce_override)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p, _, _ in self._layout)
         if self.direct_grad and need_grad:
             if self._grad_anchor is None or self._grad_anchor.device != x.device:
                 self._grad_anchor = torch.zeros((), device=x.device, requires_grad=True)
             params = [self._grad_anchor]  # one differentiable input keeps the node in the graph
         else:
-            params = [p for p, _, _ in self._layout]
-        out, extra = _DiChaViTFn.apply(self, x, cs, idx, gid, need_grad, *params)
+            ext = self._external_ids
+            params = [p for p, _, _ in self._layout if id(p) not in ext]
+        out, extra = _DiChaViTFn.apply(self, x, cs, idx, gid, need_grad, call, *params)
         if self.training:
             return out, extra
         return out
@@ -649,7 +730,7 @@ class DiChaViT(nn.Module):
         return dict(B=B, cs=cs, H=H, W=W, P=P, D=D, heads=heads, N=N, T=T, L=L, M=M, F=Fh, Lp=Lp, depth=depth,
                     arena=ar, keep=keep)
 
-    def _embed_structs(self, pl, base: int, scal: torch.Tensor, C_in: int, use_map: bool, device):
+    def _embed_structs(self, pl, base: int, scal: torch.Tensor, C_in: int, use_map: bool, device, call: dict):
         fe = self.feature_extractor
         pe = fe.patch_embed
         cfg = self.cfg
@@ -657,14 +738,14 @@ class DiChaViT(nn.Module):
         dims = _EmbedDims(pl["B"], C_in, pl["cs"], pl["H"], pl["W"], pl["P"], pl["D"])
         # TDL / CDL only enter the training output (dichavit.py:856-861); the reference still evaluates them in eval
         # mode and throws the value away -- here the kernels are simply not launched
-        l_tdl = float(cfg.ortho_loss_v1_lambda) if self.training else 0.0
-        l_cdl = float(cfg.proxy_loss_lambda) if self.training else 0.0
-        norm = getattr(self, "_pix_norm", None)
+        l_tdl = float(cfg.ortho_loss_v1_lambda) if call["training"] else 0.0
+        l_cdl = float(cfg.proxy_loss_lambda) if call["training"] else 0.0
+        norm = call["pix_norm"]
         ecfg = _EmbedCfg(l_tdl, l_cdl, float(cfg.gamma_s), float(cfg.gamma_d), float(pe.channel_scale),
-                         int(bool(cfg.reverse_pos_pairs)), int(bool(cfg.use_square)), int(self._x_is_u8))
+                         int(bool(cfg.reverse_pos_pairs)), int(bool(cfg.use_square)), int(call["x_is_u8"]))
         has_prox = hasattr(pe, "channel_emb_proxies")
         pos_map = self._pos_map(pl["W"], pl["H"], device) if use_map else None
-        ce_ptr = self._ce_override.data_ptr() if getattr(self, "_ce_override", None) is not None else \
+        ce_ptr = call["ce_override"].data_ptr() if call["ce_override"] is not None else \
             self._fptr(pe.channel_embed.weight)
         ep = _EmbedParams(self._fptr(pe.proj.weight), self._fptr(pe.proj.bias), ce_ptr,
                           self._fptr(pe.channel_emb_proxies) if has_prox else None, self._fptr(fe.cls_token),
@@ -715,7 +796,7 @@ class DiChaViT(nn.Module):
                 cache[(base, i)] = ba
         return bp, ba, xout
 
-    def _run_forward(self, x: torch.Tensor, cs: int, idx, gid, keep: bool):
+    def _run_forward(self, x: torch.Tensor, cs: int, idx, gid, keep: bool, call: dict):
         lib = _lib.lib()
         st = _lib.stream_ptr()
         dev = x.device
@@ -746,7 +827,7 @@ class DiChaViT(nn.Module):
         scal = torch.zeros(4, dtype=torch.float32, device=dev)  # tdl, cdl, extra
         # reference dichavit.py:529-530: raw pos_embed iff the token count equals the grid and w == h
         use_map = not (cs * pl["N"] == n_pos and W == H)
-        dims, ecfg, ep, eacts, pos_map = self._embed_structs(pl, base, scal, C_in, use_map, dev)
+        dims, ecfg, ep, eacts, pos_map = self._embed_structs(pl, base, scal, C_in, use_map, dev, call)
         check(lib.dcv_embed_fwd(byref(dims), byref(ecfg), byref(ep), c_void_p(x.data_ptr()),
                                 c_void_p(idx.data_ptr()) if idx is not None else None, c_void_p(gid.data_ptr()),
                                 byref(eacts), st), "dcv_embed_fwd")
@@ -772,7 +853,7 @@ class DiChaViT(nn.Module):
                                c_void_p(logits.data_ptr()) if logits is not None else None, ncls, st), "dcv_head_fwd")
         self.last_losses = {"tdl": scal[0], "cdl": scal[1], "extra": scal[2]}
         state = dict(pl=pl, arena=arena, scal=scal, x=x, idx=idx, gid=gid, feat=feat, last=last, C_in=C_in,
-                     use_map=use_map, pos_map=pos_map) if keep else None
+                     use_map=use_map, pos_map=pos_map, call=call) if keep else None
         out = logits if head is not None else feat
         return out, scal[2], state
 
@@ -786,7 +867,11 @@ class DiChaViT(nn.Module):
         pe = fe.patch_embed
         base = state["arena"].data_ptr()
         s = pl["arena"].slots
-        gflat = torch.zeros_like(self._flat)
+        # direct_grad + a live accumulation buffer (every .grad still is the view of the flat gradient of the previous
+        # backward, nothing reduced yet): the kernels accumulate on top of it -- gradient accumulation over several
+        # forward/backward passes (CHAMMI: three chunks per optimiser step) costs no extra pass over the buffer
+        in_place = self.direct_grad and self._accumulation_buffer_live()
+        gflat = self._last_gflat if in_place else torch.zeros_like(self._flat)
         gb = gflat.data_ptr()
 
         def gp(p):
@@ -826,7 +911,7 @@ class DiChaViT(nn.Module):
                                c_void_p(gp(head.weight)) if head is not None else None,
                                c_void_p(gp(head.bias)) if head is not None else None,
                                c_void_p(gp(last_blk.mlp.fc2.bias)), st), "dcv_head_bwd")
-        reducer = _GradReducer(self, gflat) if self.grad_allreduce else None
+        reducer = _GradReducer(self, gflat) if (self.grad_allreduce and self.grad_sync) else None
         if reducer:
             reducer.ready("tail", flush=True)
         goffs = self._block_param_structs()[1]
@@ -847,9 +932,14 @@ class DiChaViT(nn.Module):
                                         c_void_p(prev_bias) if prev_bias else None, st), "dcv_block_bwd")
             if reducer:
                 reducer.ready(f"block{i}")
-        dims, ecfg, ep, eacts, _ = self._embed_structs(pl, base, state["scal"], state["C_in"], state["use_map"], dev)
+        call = state["call"]
+        dims, ecfg, ep, eacts, _ = self._embed_structs(pl, base, state["scal"], state["C_in"], state["use_map"], dev, call)
         has_prox = hasattr(pe, "channel_emb_proxies")
-        eg = _EmbedGrads(gp(pe.proj.weight), gp(pe.proj.bias), gp(pe.channel_embed.weight),
+        # no channel-token gradient when the tokens are frozen (freeze_channel_emb) or were synthesised for unseen
+        # channels (eval-time leave-one-out: gid indexes the synthesised matrix, not channel_embed.weight)
+        ce_grad = gp(pe.channel_embed.weight) if (pe.channel_embed.weight.requires_grad and call["ce_override"] is None) \
+            else None
+        eg = _EmbedGrads(gp(pe.proj.weight), gp(pe.proj.bias), ce_grad,
                          gp(pe.channel_emb_proxies) if has_prox else None, gp(fe.cls_token), gp(fe.pos_embed))
         ews = _EmbedWs(wb + w["dh"], wb + w["R"], wb + w["dpos_patch"])
         if d_extra is not None:
@@ -860,20 +950,56 @@ class DiChaViT(nn.Module):
         if reducer:
             reducer.ready("embed", flush=True)
             reducer.finish()
-        self._last_gflat = gflat  # FusedAdamW consumes the flat buffer directly
+        synced = reducer is not None
+        ext = self._external_ids
         if self.direct_grad:
-            # skip autograd's 150 AccumulateGrad nodes: .grad of every parameter becomes (or accumulates) a view of the
-            # flat buffer.  Tensor hooks / DDP reducer hooks on the parameters do NOT fire in this mode.
-            views = self._grad_views(gflat)
-            for (p, _, _), v in zip(self._layout, views):
-                if not p.requires_grad:
-                    continue
-                if p.grad is None:
-                    p.grad = v
+            # skip autograd's 150 AccumulateGrad nodes: .grad of every parameter the kernels own becomes (or accumulates
+            # into) a view of the flat buffer.  Tensor hooks / DDP reducer hooks on the parameters do NOT fire in this
+            # mode.  `proxies` / `logit_scale` are left to torch autograd (the trainer's loss glue produces them).
+            if not in_place:
+                prev = self._last_gflat
+                if prev is not None and self._grads_alias(prev):
+                    prev.add_(gflat)  # a reduced buffer cannot be accumulated into by the kernels: one flat add
+                    gflat = prev
                 else:
-                    p.grad.add_(v)
+                    views = self._grad_views(gflat)
+                    fresh = True
+                    for (p, _, _), v in zip(self._layout, views):
+                        if not p.requires_grad or id(p) in ext:
+                            continue
+                        if p.grad is None:
+                            p.grad = v
+                        else:
+                            p.grad.add_(v)
+                            fresh = False
+                    if not fresh:
+                        gflat = None  # gradients live in tensors we do not own: FusedAdamW gathers them
+            self._last_gflat = gflat
+            self._gflat_synced = synced or (in_place and getattr(self, "_gflat_synced", False))
             return None
-        return [v if p.requires_grad else None for (p, _, _), v in zip(self._layout, self._grad_views(gflat))]
+        self._last_gflat = gflat  # FusedAdamW consumes the flat buffer directly when .grad still aliases it
+        self._gflat_synced = synced
+        return [v if (p.requires_grad and id(p) not in ext) else None
+                for (p, _, _), v in zip(self._layout, self._grad_views(gflat)) if id(p) not in ext]
+
+    def _grads_alias(self, g: torch.Tensor) -> bool:
+        """every trainable parameter the kernels own has .grad == its view of the flat buffer g"""
+        base = g.data_ptr()
+        ext = self._external_ids
+        for p, off, _ in self._layout:
+            if not p.requires_grad or id(p) in ext:
+                continue
+            if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                return False
+        return True
+
+    def _accumulation_buffer_live(self) -> bool:
+        g = self._last_gflat
+        if g is None or g.numel() != self._flat.numel() or g.device != self._flat.device:
+            return False
+        if self.grad_allreduce and getattr(self, "_gflat_synced", False):
+            return False  # already averaged over the ranks: adding raw local gradients would mix scales
+        return self._grads_alias(g)
 
     def _grad_views(self, gflat: torch.Tensor):
         return [gflat[off:off + n].view(p.shape) for p, off, n in self._layout]
@@ -951,8 +1077,8 @@ class _GradReducer:
 
 class _DiChaViTFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module: DiChaViT, x, cs, idx, gid, need_grad, *params):
-        out, extra, state = module._run_forward(x, cs, idx, gid, keep=need_grad)
+    def forward(ctx, module: DiChaViT, x, cs, idx, gid, need_grad, call, *params):
+        out, extra, state = module._run_forward(x, cs, idx, gid, keep=need_grad, call=call)
         ctx.module = module
         ctx.state = state
         ctx.set_materialize_grads(False)
@@ -965,8 +1091,8 @@ class _DiChaViTFn(torch.autograd.Function):
         grads = ctx.module._run_backward(ctx.state, d_out, d_extra)
         ctx.state = None
         if grads is None:  # direct_grad: gradients were written to .grad, the only input is the anchor scalar
-            return (None, None, None, None, None, None, None)
-        return (None, None, None, None, None, None, *grads)
+            return (None, None, None, None, None, None, None, None)
+        return (None, None, None, None, None, None, None, *grads)
 
 
 class ChannelViTAdapt(DiChaViT):

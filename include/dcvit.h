@@ -117,6 +117,36 @@ int dcv_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
  * gradients are scaled by min(1, max_norm / (sqrt(sumsq) + 1e-6)) as torch clip_grad_norm_ (trainer.py:1003-1004). */
 int dcv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* clip, void* stream);
+/* ---- device-resident optimiser scalars (CUDA-graph friendly: a captured step replays with the values of the
+ * current update).  dcv_optim_sched_step advances state->num_updates by one and evaluates, ON THE DEVICE,
+ *   - the learning rate of timm's CosineLRScheduler._get_lr (reference lr_schedulers.py:6-9; parameters of
+ *     configs/scheduler/cosine.yaml; cycle_mul == 1, no noise) -- t counts updates (updates_per_epoch == 0: the
+ *     lr set by step_update(num_updates) after the previous optimizer.step(), trainer.py:1009-1010) or 1-based
+ *     epochs (updates_per_epoch > 0: scheduler.step(epoch), trainer.py:344-348); t_initial <= 0: constant base_lr;
+ *   - the weight decay of utils.cosine_scheduler (utils.py:563-574) as indexed by trainer.py:1011-1019
+ *     (wd_total = epochs * updates_per_epoch entries; wd_total == 0: constant wd_base);
+ *   - Adam's bias corrections for update number state->num_updates.
+ * dcv_adamw_step_dev is dcv_adamw_step reading lr / weight decay / bias corrections from that state. ---- */
+typedef struct dcv_optim_state { /* device memory, 32 bytes; zero-filled = no update applied yet */
+  int num_updates;
+  float lr, wd, bc1, bc2_sqrt;
+  float reserved[3];
+} dcv_optim_state;
+
+typedef struct dcv_sched {
+  float base_lr, lr_min, warmup_lr_init;
+  int t_initial, warmup_t, warmup_prefix, cycle_limit;
+  float cycle_decay, k_decay;
+  int updates_per_epoch;
+  float wd_base, wd_end;
+  int wd_total;
+  float beta1, beta2;
+} dcv_sched;
+
+int dcv_optim_sched_step(dcv_optim_state* state, const dcv_sched* cfg, void* stream);
+int dcv_adamw_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float beta1, float beta2,
+                       float eps, const dcv_optim_state* state, const float* clip, void* stream);
+
 /* out[0] += sum_i g[i]^2 (n % 4 == 0; caller zeroes out) */
 int dcv_sumsq_f32(const float* g, long long n, float* out, void* stream);
 
@@ -281,6 +311,12 @@ void dcv_debug_set_nt_cluster(int cm);
 /* debug: clock64() timeline of one CTA of the attention-backward kernel into buf (>= 3*1024 int64, device);
  * NULL switches it off */
 int dcv_debug_attn_timeline(long long* buf);
+
+/* debug / tuning: instruction-stream variants of the attention kernels (same results up to the documented exp2
+ * polynomial error): 0 = scalar fp32 math, every exponential on the MUFU; 1 = packed-pair fp32 math (FFMA2 / FADD2,
+ * 3-input max); 2, 3, 4 = 1 + 2 / 3 / 4 of every 8 exponential pairs evaluated by a polynomial on the FMA pipe.
+ * A negative value leaves that kernel's mode unchanged. */
+void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode);
 
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);

@@ -398,3 +398,72 @@ def loss_and_grads(x, y, params, cfg, channels, has_head, indices=None, extra_lo
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else None) for k, v in p.items()}
     return loss.detach(), o, grads
+
+
+# ---------------------------------------------------------------------------------------------
+# optimiser schedules
+# ---------------------------------------------------------------------------------------------
+
+def timm_cosine_lr(t: int, base_lr: float, t_initial: int, lr_min: float = 0.0, warmup_t: int = 0,
+                   warmup_lr_init: float = 0.0, warmup_prefix: bool = False, cycle_mul: float = 1.0,
+                   cycle_decay: float = 1.0, cycle_limit: int = 1, k_decay: float = 1.0) -> float:
+    """CosineLRScheduler._get_lr(t) for one parameter group.  Third-party algorithm: timm (pinned 0.8.3.dev0 in the
+    reference's requirements.txt:18, absent from /root/reference and from this image), restated from its published
+    source timm/scheduler/cosine_lr.py; built by reference lr_schedulers.py:6-9 with configs/scheduler/cosine.yaml
+    and stepped at trainer.py:344-348 (per epoch, t_in_epochs) or trainer.py:1009-1010 (per update)."""
+    if t < warmup_t:
+        return warmup_lr_init + t * ((base_lr - warmup_lr_init) / warmup_t)
+    if warmup_prefix:
+        t = t - warmup_t
+    if cycle_mul != 1:
+        i = math.floor(math.log(1 - t / t_initial * (1 - cycle_mul), cycle_mul))
+        t_i = cycle_mul ** i * t_initial
+        t_curr = t - (1 - cycle_mul ** i) / (1 - cycle_mul) * t_initial
+    else:
+        i = t // t_initial
+        t_i = t_initial
+        t_curr = t - (t_initial * i)
+    lr_max = base_lr * (cycle_decay ** i)
+    if i < cycle_limit:
+        return lr_min + 0.5 * (lr_max - lr_min) * (1 + math.cos(math.pi * t_curr ** k_decay / t_i ** k_decay))
+    return lr_min
+
+
+def cosine_scheduler(base_value, final_value, epochs, niter_per_ep, warmup_epochs=0, start_warmup_value=0):
+    """utils.py:563-574, verbatim semantics (numpy table of epochs * niter_per_ep values)."""
+    import numpy as np
+
+    warmup_schedule = np.array([])
+    warmup_iters = warmup_epochs * niter_per_ep
+    if warmup_epochs > 0:
+        warmup_schedule = np.linspace(start_warmup_value, base_value, warmup_iters)
+    iters = np.arange(epochs * niter_per_ep - warmup_iters)
+    schedule = final_value + 0.5 * (base_value - final_value) * (1 + np.cos(np.pi * iters / len(iters)))
+    schedule = np.concatenate((warmup_schedule, schedule))
+    assert len(schedule) == epochs * niter_per_ep
+    return schedule
+
+
+def trainer_lr_wd_sequence(n_updates: int, updates_per_epoch: int, epochs: int, base_lr: float, wd: float,
+                           wd_end: Optional[float], sched: Optional[dict], t_in_epochs: bool) -> List[Tuple[float, float]]:
+    """(lr, weight_decay) the optimiser sees at update 1..n_updates under the reference's training loop: the epoch
+    loop calls scheduler.step(epoch) before each epoch (trainer.py:344-348; a no-op unless t_in_epochs), every batch
+    calls optimizer.step() and THEN scheduler.step_update(num_updates) (a no-op if t_in_epochs) and overwrites
+    param_group["weight_decay"] with wd_schedule[num_updates - 1] (trainer.py:1006-1019).  timm's constructor
+    starts the groups at warmup_lr_init when warmup_t > 0 (Scheduler.__init__ / CosineLRScheduler.__init__)."""
+    table = cosine_scheduler(wd, wd_end, epochs, updates_per_epoch) if wd_end is not None and wd_end > -1 else None
+    lr = base_lr
+    if sched is not None and sched.get("warmup_t", 0):
+        lr = sched.get("warmup_lr_init", 0.0)
+    cur_wd = wd
+    out = []
+    for u in range(1, n_updates + 1):
+        epoch = 1 + (u - 1) // updates_per_epoch
+        if sched is not None and t_in_epochs and (u - 1) % updates_per_epoch == 0:
+            lr = timm_cosine_lr(epoch, base_lr, **sched)
+        out.append((lr, cur_wd))
+        if sched is not None and not t_in_epochs:
+            lr = timm_cosine_lr(u, base_lr, **sched)
+        if sched is not None and table is not None:
+            cur_wd = float(table[min(u - 1, len(table) - 1)])
+    return out

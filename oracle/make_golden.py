@@ -110,6 +110,19 @@ def cases():
                                       in_channel_names=names12, num_classes=14, temperature=0.07,
                                       proxy_loss_lambda=0.1, ortho_loss_v1_lambda=1.0, gamma_s=0.5, gamma_d=2.0,
                                       reverse_pos_pairs=True), CHAMMI_MAPPER, "Allen", False, 8, 41, 42, 1.0)
+    # the BENCHED configurations at full model / image size (BASELINE.json configs[2], [3], [4]), small batch
+    ch8 = [f"c{i}" for i in range(8)]
+    out["full_c3"] = (O.OracleConfig(pretrained_model_name="small", img_size=224, patch_size=16, in_channel_names=ch8,
+                                     num_classes=161, proxy_loss_lambda=0.001, ortho_loss_v1_lambda=0.001, gamma_s=1.0,
+                                     gamma_d=4.0, reverse_pos_pairs=True, hcs_sampling_temp=1000.0),
+                      {"train": list(range(8))}, "train", True, 2, 71, 72, 1.0)
+    out["full_c4"] = (O.OracleConfig(pretrained_model_name="small", img_size=32, patch_size=8,
+                                     in_channel_names=[f"c{i}" for i in range(18)], num_classes=17,
+                                     proxy_loss_lambda=0.001, ortho_loss_v1_lambda=0.1, gamma_s=0.5, gamma_d=4.0,
+                                     reverse_pos_pairs=True, hcs_sampling_temp=0.01),
+                      {"train": list(range(18))}, "train", True, 8, 73, 74, 1.0)
+    out["full_c5"] = (O.OracleConfig(pretrained_model_name="base", img_size=224, patch_size=16, in_channel_names=ch8,
+                                     num_classes=161), {"train": list(range(8))}, "train", True, 2, 75, 76, 1.0)
     return out
 
 

