@@ -145,22 +145,38 @@ def cpu_reference_run(wname: str, steps: int, warmup: int, batch: int, seed: int
                         in_channel_names=[f"c{i}" for i in range(w["channels"])], num_classes=w["classes"],
                         enable_sample=w["sample"], hcs_sampling="lowest_cosine_prob", hcs_sampling_temp=w["hcs_temp"],
                         proxy_loss_lambda=w["l_cdl"], ortho_loss_v1_lambda=w["l_tdl"], gamma_s=w["gs"], gamma_d=w["gd"],
-                        reverse_pos_pairs=True, use_square=False)
+                        reverse_pos_pairs=True, use_square=False, temperature=w.get("temperature", 0.11111))
     set_seeds(seed, False)
-    weights = O.make_weights(oc, True, seed)
+    chunks = w.get("chunks")
+    has_head = not chunks
+    weights = O.make_weights(oc, has_head, seed)
     params = {k: v.clone().requires_grad_(True) for k, v in weights.items() if k != "adaptive_interface.0"}
     opt = torch.optim.AdamW([p for p in params.values()], lr=4e-4, weight_decay=0.04)
-    channels = list(range(w["channels"]))
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(batch, w["channels"], w["img"], w["img"], generator=g)
     y = torch.randint(0, w["classes"], (batch,), generator=g)
+    # CHAMMI: the sample batch is split over the three chunks like the real one (trainer.py:846-931)
+    parts = [(list(range(w["channels"])), 0, batch)]
+    if chunks:
+        parts, off = [], 0
+        nb = max(1, batch // len(chunks))
+        for chs, _ in chunks.values():
+            parts.append((chs, off, nb))
+            off += nb
+        batch = off
     times = []
     for it in range(warmup + steps):
+        if it == warmup:
+            random.seed(seed)  # the C' sequence of the timed steps == the one our arm times (bench `timed(..., 2025)`)
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        o = O.forward(x, params, oc, channels, training=True, has_head=True)
-        loss = F.cross_entropy(o.out, y) + o.extra_loss * 1.0
-        loss.backward()
+        for chs, off, nb in parts:
+            o = O.forward(x[off:off + nb, :len(chs)], params, oc, chs, training=True, has_head=has_head)
+            if has_head:
+                loss = F.cross_entropy(o.out, y[off:off + nb]) + o.extra_loss * 1.0
+            else:
+                loss = O.proxy_loss(params["proxies"], o.out, y[off:off + nb], (1.0 / oc.temperature) ** 0.5) + o.extra_loss * 1.0
+            loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
         if it >= warmup:
@@ -215,19 +231,33 @@ def gpu_eager_run(wname: str, batch: int, steps: int, autocast: bool, seed: int 
     return batch * steps / (e0.elapsed_time(e1) / 1000.0)
 
 
+def bench_config(w, world: int) -> dict:
+    """the `config` object of the JSON line: identical in both arms (the reference arm's bounded sample is described in
+    its cpu_baseline.sample, not here)"""
+    B = w["batch"]
+    return {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "step": "zero_grad + fwd + CE/extra loss + bwd (+NCCL grad all-reduce) + AdamW update",
+            "dcs": "seeded random C' in 1..C per step (python random seed 2025 at the start of the timed steps), same "
+                   "draws on every rank and in both arms",
+            "l2": "each step streams >5 GB of activations (>> 126 MB L2); no explicit flush"}
+
+
 def reference_arm(args, wname):
+    """The reference's own CPU path (oracle port of the PyTorch module, fp32, every host thread): exactly --steps timed
+    steps after --warmup untimed ones; each step is a bounded sample of the workload's batch (B = 4 at 224x224, 32 at
+    32x32) so that the run ends within minutes.  The DCS draws of the timed steps are the ones our arm times."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = WORKLOADS[wname]
     batch = 4 if w["img"] >= 224 else 32
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
+    if w["size"] == "base":
+        batch = 2
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     ips, secs, cores, sample = cpu_reference_run(wname, steps, warm, batch)
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1000.0 * secs / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "per_gpu_batch": w["batch"], "sample_batch": batch},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(w, args.gpus),
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -241,12 +271,17 @@ def algorithmic_flops_attn(B, L, D, bwd: bool):
 
 
 def ours(args, wname):
+    import ctypes
+
     import torch
     import torch.distributed as dist
     import torch.nn.functional as F
 
     from diverse_channel_vit_b200 import _lib
     from diverse_channel_vit_b200.dichavit import dichavit
+    from diverse_channel_vit_b200.graphs import GraphedTrainStep
+    from diverse_channel_vit_b200.optim import CosineLRSchedule, CosineWDSchedule, FusedAdamW
+    from diverse_channel_vit_b200.trainer_glue import proxy_loss as _proxy_loss  # plain torch loss glue of the trainer
 
     w = WORKLOADS[wname]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,9 +308,17 @@ def ours(args, wname):
     model.direct_grad = True  # gradients land in .grad as views of one flat buffer, no per-tensor autograd nodes
     if world > 1:
         model.enable_data_parallel(overlap=os.environ.get("DCV_DP_OVERLAP", "1") != "0")
-    from diverse_channel_vit_b200.optim import FusedAdamW
 
-    opt = FusedAdamW(model, lr=4e-4, weight_decay=0.04)  # timm/torch AdamW semantics, one launch on the flat buffers
+    # The public training-step API: one CUDA-graph launch per (chunk, batch, C') bucket (graphs.py).  DCV_GRAPHS=0
+    # falls back to ordinary launches enqueued from Python (the round-1 path) for A/B comparison.
+    use_graphs = os.environ.get("DCV_GRAPHS", "1") != "0"
+    # AdamW as the reference configures it for JUMP-CP (configs/optimizer/adamw_jumpcp.yaml): lr 4e-4, weight decay
+    # 0.04 -> 0.4 on a per-update cosine, cosine learning rate per epoch (configs/scheduler/cosine.yaml); all scalars
+    # are evaluated on the device so that the captured step replays with the current values
+    upe = 100
+    opt = FusedAdamW(model, lr=4e-4, weight_decay=0.04, device_schedule=True, updates_per_epoch=upe,
+                     lr_schedule=CosineLRSchedule(4e-4, 100, lr_min=1e-6, warmup_t=3, warmup_lr_init=1e-5, cycle_decay=0.5),
+                     wd_schedule=CosineWDSchedule(0.04, 0.4, 100, upe))
     gen = torch.Generator(device="cpu").manual_seed(2025 + rank)
     max_ch = max(len(v[0]) for v in chunks.values()) if chunks else w["channels"]
     x_host = torch.randn(B, max_ch, w["img"], w["img"], generator=gen).pin_memory()
@@ -285,35 +328,27 @@ def ours(args, wname):
     copy_stream = torch.cuda.Stream(device=dev)
     x_buf = [torch.empty_like(x_dev) for _ in range(2)]
     y_buf = [torch.empty_like(y_dev) for _ in range(2)]
-    # > 126 MB L2 flush buffer, written between timed steps is unnecessary here: one step streams several GB
-    # of activations (far larger than L2); stated in config.l2.
 
-    from diverse_channel_vit_b200.trainer_glue import proxy_loss as _proxy_loss  # plain torch loss glue of the trainer
+    def loss_glue(m, out, extra, y):
+        if chunks:
+            return _proxy_loss(m.proxies, out, y, m.scale) + extra * 1.0  # trainer.py:912-914
+        return F.cross_entropy(out, y) + extra * 1.0  # trainer.py:986-995
 
-    PREFETCH_DCS = os.environ.get("DCV_PREFETCH_DCS", "1") != "0"
+    gstep = GraphedTrainStep(model, opt, loss_fn=loss_glue)
+    mode = {"eager": not use_graphs}
 
     def step(x, y):
-        opt.zero_grad(set_to_none=True)
         if chunks:  # trainer.py:846-931: one forward/backward per chunk, one optimiser step
-            off = 0
-            for name, (chs, nb) in chunks.items():
-                xc = x[off:off + nb, :len(chs)].contiguous()
-                out, extra = model(xc, name)
-                loss = _proxy_loss(model.proxies, out, y[off:off + nb], model.scale) + extra * 1.0  # trainer.py:912-914
-                loss.backward()
+            off, names = 0, list(chunks)
+            for i, name in enumerate(names):
+                chs, nb = chunks[name]
+                xs, ys = gstep.input_buffers(name, (nb, len(chs), w["img"], w["img"]), x.dtype, dev)
+                xs.copy_(x[off:off + nb, :len(chs)])
+                ys.copy_(y[off:off + nb])
+                loss = gstep(xs, ys, name, last=i == len(names) - 1, eager=mode["eager"])
                 off += nb
-        else:
-            out, extra = model(x, "train")
-            loss = F.cross_entropy(out, y) + extra * 1.0  # trainer.py:986-995
-            loss.backward()
-        opt.step()
-        if PREFETCH_DCS:  # next step's (first) channel draw: same RNG sequence, enqueued before the host reads the loss
-            if chunks:
-                first = next(iter(chunks))
-                model.prefetch_dcs(first, len(chunks[first][0]))
-            else:
-                model.prefetch_dcs("train", x.shape[1])
-        return loss
+            return loss
+        return gstep(x, y, "train", eager=mode["eager"])
 
     def barrier():
         if world > 1:
@@ -321,9 +356,8 @@ def ours(args, wname):
         torch.cuda.synchronize()
 
     def timed(nsteps, e2e: bool, seed: int):
-        """returns max-over-ranks elapsed ms (CUDA events) and per-step host-visible losses"""
+        """returns max-over-ranks elapsed ms (CUDA events)"""
         random.seed(seed)  # DCS draws: identical on every rank and in every pass
-        model.feature_extractor.patch_embed._prefetched = None  # a draw prefetched by the previous pass is stale
         torch.manual_seed(seed + 2)
         torch.cuda.manual_seed_all(seed + 4)
         barrier()
@@ -366,19 +400,37 @@ def ours(args, wname):
         barrier()
         return ms.item()
 
+    def launches():
+        return _lib.launch_count() + gstep.kernel_launches
+
     K, W = args.steps, args.warmup
+    pe = model.feature_extractor.patch_embed
     # warm-up: one full-channel step first (largest shape: activation / workspace arenas reach their final size,
-    # every kernel attribute is set), then W >= 3 steps of the workload itself
-    model.feature_extractor.patch_embed.enable_sample = False
+    # every kernel attribute is set), every (chunk, C') graph captured, then W >= 3 steps of the workload itself
+    pe.enable_sample = False
     timed(1, False, 1)
-    model.feature_extractor.patch_embed.enable_sample = w["sample"]
+    pe.enable_sample = w["sample"]
+    t_cap = time.time()
+    n_graphs = 0
+    if use_graphs:
+        if chunks:
+            names = list(chunks)
+            off = 0
+            for i, name in enumerate(names):
+                chs, nb = chunks[name]
+                n_graphs += gstep.precapture(x_dev[off:off + nb, :len(chs)].contiguous(), y_dev[off:off + nb], name,
+                                             first=i == 0, last=i == len(names) - 1)
+                off += nb
+        else:
+            n_graphs += gstep.precapture(x_dev, y_dev, "train")
+    t_cap = time.time() - t_cap
     timed(max(W, 3), False, 1)
     clk = ClockSampler(local) if rank == 0 else None
-    l0 = _lib.launch_count()
+    l0, g0 = launches(), gstep.graph_launches
     t0 = time.time()
     ms = timed(K, False, 2025)
     t1 = time.time()
-    launches = _lib.launch_count() - l0
+    n_launch, n_glaunch = launches() - l0, gstep.graph_launches - g0
     clocks = clk.stop(t0, t1) if clk else None
     value = world * B * K / (ms / 1000.0)
 
@@ -386,40 +438,55 @@ def ours(args, wname):
     ms_e2e = timed(K, True, 2025)
     e2e_value = world * B * K / (ms_e2e / 1000.0)
 
+    # sustained pass: the same workload for >= 3 s (the --steps pass is a 0.2 s burst at boost clocks)
+    ks = max(K, int(3000.0 / (ms / K)) + 1)
+    clk2 = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    ms_sus = timed(ks, False, 2025)
+    t1 = time.time()
+    clocks_sus = clk2.stop(t0, t1) if clk2 else None
+    sustained = {"value": world * B * ks / (ms_sus / 1000.0), "unit": UNIT, "steps": ks, "ms_per_step": ms_sus / ks,
+                 "seconds": ms_sus / 1000.0, "clocks": clocks_sus}
+
     # full-channel (C' = C, no sampling) reference point
-    model.feature_extractor.patch_embed.enable_sample = False
+    pe.enable_sample = False
     timed(2, False, 1)
     kf = max(3, K // 2)
     ms_full = timed(kf, False, 2025)
     full_value = world * B * kf / (ms_full / 1000.0)
 
-    # ---- per-kernel-class breakdown, live CUDA events (separate pass; rank 0 reports) ----
+    # ---- per-kernel-class breakdown, live CUDA events around every launch (the built-in profiler sits in the host
+    # launchers, so these passes run the identical step sequence as ordinary launches, not as a graph replay) ----
     lib = _lib.lib()
-    import ctypes
-
     ntags = lib.dcv_profile_num_tags()
     lib.dcv_profile_tag_name.restype = ctypes.c_char_p
-    names = [lib.dcv_profile_tag_name(i).decode() for i in range(ntags)]
+    names_t = [lib.dcv_profile_tag_name(i).decode() for i in range(ntags)]
     msb = (ctypes.c_double * ntags)()
     cnt = (ctypes.c_longlong * ntags)()
     kp = max(2, min(K, 5))
+    mode["eager"] = True
+    timed(1, False, 1)
     barrier()
     lib.dcv_profile_start()
     ms_prof = timed(kp, False, 2025)  # still full channels: L fixed, algorithmic work per launch exact
     lib.dcv_profile_stop(msb, cnt, ntags)
-    prof = {names[i]: {"ms_per_step": msb[i] / kp, "launches_per_step": cnt[i] / kp} for i in range(ntags) if cnt[i]}
-    model.feature_extractor.patch_embed.enable_sample = w["sample"]
+    prof = {names_t[i]: {"ms_per_step": msb[i] / kp, "launches_per_step": cnt[i] / kp} for i in range(ntags) if cnt[i]}
+    pe.enable_sample = w["sample"]
     # same breakdown over the timed workload itself (seeded DCS draws, variable L)
     barrier()
     lib.dcv_profile_start()
     timed(K, False, 2025)
     lib.dcv_profile_stop(msb, cnt, ntags)
-    prof_dcs = {names[i]: round(msb[i] / K, 4) for i in range(ntags) if cnt[i]}
+    prof_dcs = {names_t[i]: round(msb[i] / K, 4) for i in range(ntags) if cnt[i]}
+    # eager (no graphs) end-to-end pass of the same workload: what the graph launch buys
+    ms_e2e_eager = timed(K, True, 2025)
+    mode["eager"] = not use_graphs
 
     D = model.dim
     npatch = (w["img"] // w["patch"]) ** 2
     L = 1 + (max_ch if chunks else w["channels"]) * npatch
     depth = len(model.feature_extractor.blocks)
+    heads = model.feature_extractor.num_heads
     # sub-batches of one (full-channel) step: (images, tokens per image)
     subs = [(nb, 1 + len(chs) * npatch) for chs, nb in chunks.values()] if chunks else [(B, L)]
     # algorithmic FLOPs per STEP and kernel class for the work actually performed (the last block only
@@ -459,7 +526,6 @@ def ours(args, wname):
     # memory-bound kernel classes: algorithmic bytes per STEP / summed CUDA-event time, against the
     # measured HBM copy bandwidth.  Full-size calls only are counted (the last block's CLS-row calls move KBs).
     hbm_peak = float(peaks.get("hbm_gbs", 6550.0))
-    F = 4 * D
     by = {k: 0.0 for k in ("ln_fwd", "ln_bwd", "colsum", "attn_bwd_fin", "im2col", "tdl", "embed_bwd")}
     for nb, Lc in subs:
         M = nb * Lc
@@ -487,6 +553,15 @@ def ours(args, wname):
             dist.destroy_process_group()
         return
 
+    # ---- attention kernels next to the library kernel on the same box (torch SDPA, cuDNN backend), at this
+    # workload's full-channel shape: CUDA events, 20 launches each after 5 warm-ups ----
+    sdpa = None
+    if world == 1 and not args.no_eager:
+        try:
+            sdpa = attention_vs_sdpa(subs[-1][0], subs[-1][1], heads)
+        except Exception as ex:
+            sdpa = {"error": repr(ex)[:200]}
+
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only ----
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -498,7 +573,7 @@ def ours(args, wname):
     eager = None
     if world == 1 and not args.no_eager:
         try:
-            del model, opt
+            del gstep, model, opt
             torch.cuda.empty_cache()
             eb = B
             while True:  # the reference materialises [B,H,L,L] fp32 probabilities per layer: halve the batch on OOM
@@ -510,25 +585,29 @@ def ours(args, wname):
                     if eb <= 4:
                         raise
                     eb //= 2
-            eager = {"what": "oracle restatement of the reference run eagerly by PyTorch on this GPU (cuBLAS/cuDNN/ATen), "
-                             "full channels; compare with full_channels.value",
+            eager = {"what": "the reference algorithm run eagerly by PyTorch on this GPU (cuBLAS/cuDNN/ATen), full channels; "
+                             "compare with full_channels.value",
+                     "source": "port (oracle restatement of the reference's ATen call sequence: the reference checkout and "
+                               "its timm / omegaconf dependencies do not exist on the GPU box)",
                      "batch": eb, "fp32_images_per_s": r32, "bf16_autocast_images_per_s": r16}
         except Exception as ex:  # report, do not fail the bench
             eager = {"error": repr(ex)[:200]}
 
     h2d = x_host.numel() * 4 + y_host.numel() * 8
+    cfg = bench_config(w, world)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "step": "zero_grad + fwd + CE/extra loss + bwd (+NCCL grad all-reduce) + fused flat-buffer AdamW",
-                   "dcs": "seeded random C' in 1..C per step (python random seed 2025), same draws on every rank",
-                   "l2": "each step streams >5 GB of activations (>> 126 MB L2); no explicit flush"},
+        "data": "synthetic", "config": cfg,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / K},
-        "gpu_launches": int(launches),
+                "ms_per_step": ms_e2e / K, "without_graphs_ms_per_step": ms_e2e_eager / K},
+        "gpu_launches": int(n_launch),
+        "graph_launches": int(n_glaunch),
+        "graphs": {"enabled": use_graphs, "captured": n_graphs, "capture_seconds": round(t_cap, 2),
+                   "note": "one cudaGraphLaunch per (chunk, C') bucket and micro-step; gpu_launches counts the kernels "
+                           "of this library executed by those replays"},
         "clocks": clocks,
+        "sustained": sustained,
         "full_channels": {"value": full_value, "unit": UNIT, "ms_per_step": ms_full / kf, "tokens": L,
                           "model_tflops": None},
         "roofline": roof,
@@ -537,6 +616,7 @@ def ours(args, wname):
         "attn_tflops": attn_tf, "attn_frac_of_peak": (attn_tf / peak_tf) if attn_tf else None,
         "gemm_tflops": gemm_tf, "gemm_frac_of_peak": (gemm_tf / peak_tf) if gemm_tf else None,
         "hbm_kernels": hbm_kernels,
+        "attention_vs_sdpa": sdpa,
         "cpu_baseline": cpu,
         "torch_eager_gpu": eager,
     }
@@ -550,6 +630,154 @@ def ours(args, wname):
         dist.destroy_process_group()
 
 
+def attention_vs_sdpa(B: int, L: int, H: int):
+    """dcv_attn_fwd / dcv_attn_bwd (prep + main + finish) against torch.nn.functional.scaled_dot_product_attention with
+    the cuDNN backend (the library kernel for this op on Blackwell), forward and backward, same B / L / H, bf16."""
+    import torch
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    from diverse_channel_vit_b200 import kernels as Kn
+
+    dev = torch.device("cuda")
+    D = H * 64
+    qkv = torch.randn(B * L, 3 * D, device=dev).bfloat16()
+    do = torch.randn(B * L, D, device=dev).bfloat16()
+
+    def bench(fn, n=20, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+
+    o = torch.empty(B * L, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, Kn.lpad(L), device=dev)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, H, Kn.lpad(L), device=dev)
+    acc = torch.empty(B, H, L, 64, device=dev)
+    ours_f = bench(lambda: Kn.attn_fwd(qkv, B, L, H, o=o, lse2=lse))
+    ours_b = bench(lambda: Kn.attn_bwd(qkv, o, do, lse, B, L, H, dqkv=dqkv, delta=delta, dq_acc=acc))
+    q, k, v = (t.contiguous().requires_grad_(True) for t in qkv.reshape(B, L, 3, H, 64).permute(2, 0, 3, 1, 4))
+    with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+        lib_f = bench(lambda: torch.nn.functional.scaled_dot_product_attention(q.detach(), k.detach(), v.detach()))
+        out = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+        gout = torch.randn_like(out)
+        lib_b = bench(lambda: torch.autograd.grad(out, (q, k, v), gout, retain_graph=True))
+    ff, fb = 4.0 * B * H * L * L * 64, 8.0 * B * H * L * L * 64
+    return {"shape": {"B": B, "L": L, "H": H, "head_dim": 64},
+            "fwd_us": {"ours": ours_f, "sdpa_cudnn": lib_f}, "bwd_us": {"ours_prep_main_finish": ours_b, "sdpa_cudnn": lib_b},
+            "fwd_tflops": {"ours": ff / ours_f / 1e6, "sdpa_cudnn": ff / lib_f / 1e6},
+            "bwd_tflops": {"ours": fb / ours_b / 1e6, "sdpa_cudnn": fb / lib_b / 1e6}}
+
+
+def eval_mode(args, wname):
+    """`--mode eval`: inference forward of the drop-in module (model.eval(), torch.inference_mode; reference
+    trainer.py:385-472), all channels, BASELINE.json configs[4] "eval".  Same JSON contract, metric = eval images/sec."""
+    import torch
+    import torch.distributed as dist
+
+    from diverse_channel_vit_b200 import _lib
+    from diverse_channel_vit_b200.dichavit import dichavit
+
+    w = WORKLOADS[wname]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    set_seeds(2025, True)
+    chunks = w.get("chunks")
+    if chunks:
+        raise SystemExit("--mode eval: use jumpcp / so2sat / vitb")
+    model = dichavit(model_cfg(w), mapper={"train": list(range(w["channels"]))}).to(dev).eval()
+    B = w["batch"] * 4  # inference keeps no activations: a larger batch fills the GPU
+    gen = torch.Generator(device="cpu").manual_seed(2025 + rank)
+    x_host = torch.randn(B, w["channels"], w["img"], w["img"], generator=gen).pin_memory()
+    x_dev = x_host.to(dev)
+    x_buf = [torch.empty_like(x_dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        with torch.inference_mode():
+            if e2e:
+                main = torch.cuda.current_stream()
+                ready = [torch.cuda.Event(), torch.cuda.Event()]
+                freed = [torch.cuda.Event(), torch.cuda.Event()]
+                for sl in range(2):
+                    freed[sl].record(main)
+
+                def upload(i):
+                    sl = i & 1
+                    copy_stream.wait_event(freed[sl])
+                    with torch.cuda.stream(copy_stream):
+                        x_buf[sl].copy_(x_host, non_blocking=True)
+                        ready[sl].record(copy_stream)
+
+                upload(0)
+                for i in range(n):
+                    sl = i & 1
+                    main.wait_event(ready[sl])
+                    if i + 1 < n:
+                        upload(i + 1)
+                    out = model(x_buf[sl], "train")
+                    freed[sl].record(main)
+                    out.argmax(dim=1).cpu()  # D2H of the predictions
+            else:
+                for _ in range(n):
+                    model(x_dev, "train")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    timed(W, False)
+    clk = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    t0 = time.time()
+    ms = timed(K, False)
+    t1 = time.time()
+    n_launch = _lib.launch_count() - l0
+    clocks = clk.stop(t0, t1) if clk else None
+    timed(2, True)
+    ms_e2e = timed(K, True)
+    if rank == 0:
+        D = model.dim
+        npatch = (w["img"] // w["patch"]) ** 2
+        L = 1 + w["channels"] * npatch
+        depth = len(model.feature_extractor.blocks)
+        fwd = B * (2.0 * (L - 1) * w["patch"] ** 2 * D + depth * (24.0 * L * D * D + 4.0 * L * L * D) + 2.0 * D * w["classes"])
+        line = {"metric": "eval images/sec (fwd)", "value": world * B * K / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": w["desc"] + " -- EVAL (inference forward, all channels)", "per_gpu_batch": B,
+                           "global_batch": B * world, "parallelism": f"dp{world}"},
+                "e2e": {"value": world * B * K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                        "d2h_bytes_per_step": B * 8, "ms_per_step": ms_e2e / K},
+                "gpu_launches": int(n_launch), "clocks": clocks,
+                "model_tflops": fwd * world / (ms / K * 1e-3) / 1e12}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -558,7 +786,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="jumpcp", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU comparison leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU / SDPA comparison legs")
+    ap.add_argument("--mode", default="train", choices=["train", "eval"], help="eval: inference forward (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args, args.workload)
@@ -567,7 +796,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    ours(args, args.workload)
+    if args.mode == "eval":
+        eval_mode(args, args.workload)
+    else:
+        ours(args, args.workload)
 
 
 if __name__ == "__main__":

@@ -41,7 +41,7 @@ __device__ long long* g_fwd_timeline = nullptr;
 #else
 #define TLF(role, it, pt) ((void)tl)
 #endif
-static int g_fwd_mode = 1;
+static int g_fwd_mode = 2;
 void debug_set_attn_fwd_mode(int m) { g_fwd_mode = m; }
 int debug_fwd_timeline(long long* buf) {
   DCV_CUDA(cudaMemcpyToSymbol(g_fwd_timeline, &buf, sizeof(buf)));
@@ -66,9 +66,7 @@ constexpr int kFwdSmem = kTq * kHd * 2 + kFwdStages * 2 * kTk * kHd * 2 + 1024 +
 //               as S_j has completed, the V slot after PV_j.
 // PK: packed-pair fp32 math (FFMA2 / FADD2) and 3-input max in the softmax; PM: 8-bit mask over the pairs of every group
 // of 8 score pairs whose exponentials are evaluated on the FMA pipe (exp2_poly_f32x2) instead of the MUFU.
-// WA: one mbarrier arrival per softmax warp (elected lane after __syncwarp) instead of one per thread, and P goes to
-// TMEM in two halves so that the first tcgen05.st overlaps the second half of the exponentials.
-template <bool PK, int PM, bool WA>
+template <bool PK, int PM>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -109,8 +107,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_consumed, WA ? 4 : 128);
-    mbar_init(p_full, WA ? 4 : 128);
+    mbar_init(s_consumed, 128);
+    mbar_init(p_full, 128);
     mbar_init(p_free, 1);
     fence_barrier_init();
   }
@@ -201,12 +199,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
       tmem_ld32(tS + lane_base + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
       tmem_ld_wait();
       tc_fence_before();
-      if constexpr (WA) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_consumed);
-      } else {
-        mbar_arrive(s_consumed);  // S_{j+1} may overwrite tS
-      }
+      mbar_arrive(s_consumed);  // S_{j+1} may overwrite tS
       TLF(1, j, 2);
       if (tail) {
 #pragma unroll
@@ -277,15 +270,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
           }
           if (i & 1) sum_b = add_f32x2(sum_b, pr); else sum_a = add_f32x2(sum_a, pr);
           sr[i] = pack_bf16(p0, p1);
-          if (WA && i == 31) {  // first half of P (key columns 0..63) -> TMEM while the second half is computed
-            if (!pv_done) {
-              mbar_wait(p_free, (j - 1) & 1);
-              tc_fence_after();
-              pv_done = true;
-            }
-            tmem_st16(tP + lane_base, *reinterpret_cast<uint32_t(*)[16]>(&sr[0]));
-            tmem_st16(tP + lane_base + 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[16]));
-          }
         }
         float s0, s1;
         unpack_f32x2(add_f32x2(sum_a, sum_b), s0, s1);
@@ -308,16 +292,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
         tc_fence_after();
       }
 #pragma unroll
-      for (int c = (WA && PK) ? 2 : 0; c < 4; ++c)
-        tmem_st16(tP + lane_base + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[c * 16]));
+      for (int c = 0; c < 4; ++c) tmem_st16(tP + lane_base + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[c * 16]));
       tmem_st_wait();
       tc_fence_before();
-      if constexpr (WA) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-      } else {
-        mbar_arrive(p_full);
-      }
+      mbar_arrive(p_full);
       TLF(1, j, 5);
     }
 
@@ -366,14 +344,11 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
   using KernelFn = void (*)(const CUtensorMap, const AttnFwdParams);
   KernelFn kern;
   switch (g_fwd_mode) {
-    case 0: kern = attn_fwd_kernel<false, 0, false>; break;
-    case 1: kern = attn_fwd_kernel<true, 0, false>; break;
-    case 2: kern = attn_fwd_kernel<true, 0x88, false>; break;  // 2 of 8 pairs on the FMA pipe
-    case 3: kern = attn_fwd_kernel<true, 0xA4, false>; break;  // 3 of 8
-    case 4: kern = attn_fwd_kernel<true, 0xAA, false>; break;  // 4 of 8
-    case 5: kern = attn_fwd_kernel<true, 0, true>; break;
-    case 6: kern = attn_fwd_kernel<true, 0x88, true>; break;
-    default: kern = attn_fwd_kernel<true, 0xA4, true>; break;
+    case 0: kern = attn_fwd_kernel<false, 0>; break;
+    case 1: kern = attn_fwd_kernel<true, 0>; break;
+    case 2: kern = attn_fwd_kernel<true, 0x88>; break;  // 2 of 8 pairs on the FMA pipe (default: fastest measured)
+    case 3: kern = attn_fwd_kernel<true, 0xA4>; break;  // 3 of 8
+    default: kern = attn_fwd_kernel<true, 0xAA>; break; // 4 of 8
   }
   DCV_TRY_SMEM_ATTR(kern, kFwdSmem);
   AttnFwdParams p;

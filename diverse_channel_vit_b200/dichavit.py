@@ -236,37 +236,60 @@ class PatchEmbedPerChannel(nn.Module):
         chan = self.chunk_channels(chunk_name, device)
         if chan.numel() != n_in:
             raise ValueError(f"x has {n_in} channels but mapper['{chunk_name}'] lists {chan.numel()}")
-        if not (self.training and self.enable_sample):
+        draw = self.draw_host(chunk_name, n_in)
+        if draw is None:
             return n_in, None, chan.to(torch.int32)
+        return self.select_device(chunk_name, device, draw)
+
+    def draw_host(self, chunk_name: str, n_in: int) -> Optional[dict]:
+        """The host half of DCS (reference dichavit.py:127-174): the python `random` draws, in the reference's order.
+        None: no sampling (eval mode / enable_sample off).  The device half (select_device) is what a captured CUDA
+        graph replays; the host half decides which (C') graph to launch."""
+        if not (self.training and self.enable_sample):
+            return None
         mode = self.cfg.hcs_sampling
         c_new = random.randint(1, n_in)
         if mode == "none" or mode is None:
             cur = random.sample(list(self.mapper[chunk_name]), k=c_new)
             pos = [list(self.mapper[chunk_name]).index(c) for c in cur]
-            idx = torch.tensor(pos, dtype=torch.int32, device=device)
-            return c_new, idx, torch.tensor(cur, dtype=torch.int32, device=device)
+            return dict(mode="none", c_new=c_new, pos=pos, cur=cur)
         if mode == "hcs_per_sample":
             raise ValueError("hcs_per_sample not implemented!")  # as the reference, dichavit.py:394-395
         if mode not in ("lowest_cosine_prob", "lowest_cosine", "highest_cosine"):
             raise NotImplementedError(f"hcs_sampling='{mode}' is outside the DiChaViT hot path")
+        return dict(mode=mode, c_new=c_new, anchor=random.randint(0, n_in - 1))
+
+    def select_device(self, chunk_name: str, device, draw: dict, anchor_dev: Optional[torch.Tensor] = None,
+                      pos_dev: Optional[torch.Tensor] = None):
+        """The device half of DCS (reference dichavit.py:176-216): cosine to the anchor, softmax, torch.multinomial on
+        the device generator (the reference's own ATen calls: bit-identical indices for a given RNG state), anchor
+        fix-up, counter.  `anchor_dev` (int64 [1]) / `pos_dev` (int32 [C']): read the host draw from device memory
+        instead of baking it into the launches -- what the captured-graph step does."""
+        chan = self.chunk_channels(chunk_name, device)
+        c_new, mode = draw["c_new"], draw["mode"]
+        if mode == "none":
+            idx = pos_dev if pos_dev is not None else torch.tensor(draw["pos"], dtype=torch.int32, device=device)
+            gid = chan[idx.long()].to(torch.int32) if pos_dev is not None else \
+                torch.tensor(draw["cur"], dtype=torch.int32, device=device)
+            return c_new, idx, gid
         with torch.no_grad():
-            anchor = random.randint(0, n_in - 1)
             emb = self.channel_embed.weight[chan]
             emb_n = F.normalize(emb, p=2, dim=-1)
-            cosine = torch.einsum("c d, e d -> c e", emb_n, emb_n)[anchor]
+            cos_all = torch.einsum("c d, e d -> c e", emb_n, emb_n)
+            cosine = cos_all.index_select(0, anchor_dev)[0] if anchor_dev is not None else cos_all[draw["anchor"]]
             if mode == "lowest_cosine_prob":
                 prob = F.softmax((1 - cosine) / self.cfg.hcs_sampling_temp, dim=-1)
                 indices = torch.multinomial(prob, c_new, replacement=False)
             else:
                 indices = torch.topk(cosine, k=c_new, largest=(mode == "highest_cosine"))[1]
             # `if anchor not in indices: indices[-1] = anchor` (dichavit.py:201-202), on the device
-            anchor_t = torch.full((), anchor, dtype=indices.dtype, device=device)
-            last = torch.where((indices == anchor).any(), indices[-1], anchor_t)
+            anchor_t = anchor_dev[0] if anchor_dev is not None else \
+                torch.full((), draw["anchor"], dtype=indices.dtype, device=device)
+            last = torch.where((indices == anchor_t).any(), indices[-1], anchor_t)
             indices = torch.cat((indices[:-1], last[None]))
             gid = chan[indices]
             self.counter.add(gid)
         return c_new, indices.to(torch.int32), gid.to(torch.int32)
-
 
     def prefetch(self, chunk_name: str, n_in: int, device) -> None:
         """Draw the NEXT forward's DCS selection now (same RNG calls, just earlier) so that the ~20 tiny sampling
@@ -449,6 +472,7 @@ class DiChaViT(nn.Module):
         self._plan_cache: Dict[tuple, dict] = {}
         self._bp_cache = None
         self.direct_grad = False  # see _DiChaViTFn.backward
+        self._static_gflat: Optional[torch.Tensor] = None  # set by graphs.GraphedTrainStep
         self.grad_sync = True     # data parallel: all-reduce in this backward (False inside no_sync())
         self._grad_anchor: Optional[torch.Tensor] = None
         self._last_gflat: Optional[torch.Tensor] = None
@@ -492,7 +516,7 @@ class DiChaViT(nn.Module):
     def __getstate__(self):
         st = dict(self.__dict__)
         st.update(_flat=None, _bflat=None, _bflat_version=-1, _layout=[], _groups=[], _pos_maps={}, _plan_cache={},
-                  _bp_cache=None, _grad_anchor=None, _last_gflat=None, _comm_stream=None, _pg=None, _arena_bytes={},
+                  _bp_cache=None, _grad_anchor=None, _last_gflat=None, _static_gflat=None, _comm_stream=None, _pg=None, _arena_bytes={},
                   _ws_bytes={}, last_losses={}, _dp_synced_ptr=0, _off={})
         return st
 
@@ -501,6 +525,8 @@ class DiChaViT(nn.Module):
 
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
+        memo[id(self.cfg)] = self.cfg  # the config is shared, not copied (read-only by convention; attr-dict configs
+        #                                whose __getattr__ raises KeyError cannot be deep-copied at all)
         for k, v in self.__getstate__().items():
             new.__dict__[k] = copy.deepcopy(v, memo)  # Parameter.__deepcopy__ clones: no view of our flat buffer survives
         return new
@@ -870,8 +896,9 @@ class DiChaViT(nn.Module):
         # direct_grad + a live accumulation buffer (every .grad still is the view of the flat gradient of the previous
         # backward, nothing reduced yet): the kernels accumulate on top of it -- gradient accumulation over several
         # forward/backward passes (CHAMMI: three chunks per optimiser step) costs no extra pass over the buffer
-        in_place = self.direct_grad and self._accumulation_buffer_live()
-        gflat = self._last_gflat if in_place else torch.zeros_like(self._flat)
+        static = getattr(self, "_static_gflat", None)  # captured-graph step: one module-owned buffer, zeroed by the graph
+        in_place = static is not None or (self.direct_grad and self._accumulation_buffer_live())
+        gflat = static if static is not None else (self._last_gflat if in_place else torch.zeros_like(self._flat))
         gb = gflat.data_ptr()
 
         def gp(p):
@@ -952,6 +979,10 @@ class DiChaViT(nn.Module):
             reducer.finish()
         synced = reducer is not None
         ext = self._external_ids
+        if static is not None:  # every .grad already is its view of the static buffer (graphs.py)
+            self._last_gflat = gflat
+            self._gflat_synced = False
+            return None
         if self.direct_grad:
             # skip autograd's 150 AccumulateGrad nodes: .grad of every parameter the kernels own becomes (or accumulates
             # into) a view of the flat buffer.  Tensor hooks / DDP reducer hooks on the parameters do NOT fire in this

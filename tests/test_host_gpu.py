@@ -215,6 +215,7 @@ def test_device_resident_schedule_equals_reference_training_loop(t_in_epochs):
                           wd_schedule=CosineWDSchedule(0.04, 0.4, epochs, upe))
 
     oa, ob = mk(ma, True), mk(mb, False)
+    mb._ensure_flat(x.device)  # mb never runs a forward here: it is fed ma's gradients
     u = 0
     for epoch in range(1, epochs + 1):
         ob.step_epoch(epoch)
