@@ -658,7 +658,7 @@ def attention_vs_sdpa(B: int, L: int, H: int):
     o = torch.empty(B * L, D, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, H, Kn.lpad(L), device=dev)
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty(B, H, Kn.lpad(L), device=dev)
+    delta = Kn.delta_ws(B, H, L, dev)
     acc = torch.empty(B, H, L, 64, device=dev)
     ours_f = bench(lambda: Kn.attn_fwd(qkv, B, L, H, o=o, lse2=lse))
     ours_b = bench(lambda: Kn.attn_bwd(qkv, o, do, lse, B, L, H, dqkv=dqkv, delta=delta, dq_acc=acc))

@@ -59,6 +59,128 @@ struct AttnFwdParams {
 constexpr int kFwdStages = 2;
 constexpr int kFwdSmem = kTq * kHd * 2 + kFwdStages * 2 * kTk * kHd * 2 + 1024 + 128;
 
+struct FwdBars {
+  uint64_t *s_full, *s_consumed, *p_full, *p_free;
+};
+
+// One KV tile of a softmax thread (query row = TMEM lane): NC = number of 32-key chunks of the tile that hold keys --
+// 4 for every tile but a ragged last one, whose S MMA only covers ceil16(valid keys) columns and whose PV MMA only
+// those K steps.  A compile-time NC keeps the hot NC = 4 instance one straight-line block (a run-time chunk guard
+// inside the unrolled body cost 14 % of the kernel: the scheduler no longer interleaved the chunks).
+template <int NC, bool PK, int PM>
+__device__ __forceinline__ void fwd_softmax_tile(int j, int L, const FwdBars& bars, uint32_t tS, uint32_t tP, uint32_t tO,
+                                                 uint32_t lane_base, float sl2, float& m, float& l, long long* tl) {
+  const int kv0 = j * kTk;
+  const bool tail = kv0 + kTk > L;
+  TLF(1, j, 0);
+  mbar_wait(bars.s_full, j & 1);
+  tc_fence_after();
+  TLF(1, j, 1);
+  uint32_t sr[32 * NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) tmem_ld32(tS + lane_base + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&sr[32 * c]));
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(bars.s_consumed);  // S_{j+1} may overwrite tS
+  TLF(1, j, 2);
+  if (tail) {
+#pragma unroll
+    for (int i = 0; i < 32 * NC; ++i)
+      if (kv0 + i >= L) sr[i] = 0xff800000u;  // -inf
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+  if constexpr (PK) {
+#pragma unroll
+    for (int i = 0; i < 32 * NC; i += 8) {
+      mx0 = fmax3(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+      mx1 = fmax3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+      mx2 = fmax3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+      mx3 = fmax3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32 * NC; i += 4) {
+      mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
+      mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+      mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
+      mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+    }
+  }
+  const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+  const bool grow = mx > m + 8.0f;  // first tile: m = -inf -> true
+  bool pv_done = j == 0;            // has this thread observed the completion of PV_{j-1} ?
+  if (__any_sync(0xffffffffu, grow)) {
+    const float alpha = grow ? fast_exp2(m - mx) : 1.0f;  // exp2(-inf) = 0 on the first tile
+    if (grow) {
+      m = mx;
+      l *= alpha;
+    }
+    if (j > 0) {  // rescale the O accumulator in TMEM (warp-collective; lanes that did not grow use 1)
+      mbar_wait(bars.p_free, (j - 1) & 1);
+      tc_fence_after();
+      pv_done = true;
+#pragma unroll
+      for (int c = 0; c < kHd / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + lane_base + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st16(tO + lane_base + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+        tmem_st16(tO + lane_base + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+      }
+    }
+  }
+  TLF(1, j, 3);
+  // exponentials in place (S_{j+1} and PV_{j-1} run on the tensor pipe meanwhile)
+  if constexpr (PK) {
+    const uint64_t sl2x2 = pack_f32x2(sl2, sl2), negm = pack_f32x2(-m, -m);
+    uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = sum_a;
+#pragma unroll
+    for (int i = 0; i < 16 * NC; ++i) {
+      const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sl2x2, negm);
+      uint64_t pr;
+      float p0, p1;
+      if ((PM >> (i & 7)) & 1) {
+        pr = exp2_poly_f32x2(x);
+        unpack_f32x2(pr, p0, p1);
+      } else {
+        unpack_f32x2(x, p0, p1);
+        p0 = fast_exp2(p0);
+        p1 = fast_exp2(p1);
+        pr = pack_f32x2(p0, p1);
+      }
+      if (i & 1) sum_b = add_f32x2(sum_b, pr); else sum_a = add_f32x2(sum_a, pr);
+      sr[i] = pack_bf16(p0, p1);
+    }
+    float s0, s1;
+    unpack_f32x2(add_f32x2(sum_a, sum_b), s0, s1);
+    l += s0 + s1;
+  } else {
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32 * NC; i += 2) {
+      const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), sl2, -m));
+      const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), sl2, -m));
+      sum0 += p0;
+      sum1 += p1;
+      sr[i >> 1] = pack_bf16(p0, p1);
+    }
+    l += sum0 + sum1;
+  }
+  TLF(1, j, 4);
+  if (!pv_done) {  // PV_{j-1} has finished reading P_{j-1}
+    mbar_wait(bars.p_free, (j - 1) & 1);
+    tc_fence_after();
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) tmem_st16(tP + lane_base + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[c * 16]));
+  tmem_st_wait();
+  tc_fence_before();
+  mbar_arrive(bars.p_full);
+  TLF(1, j, 5);
+}
+
 // Pipeline inside one CTA (a second CTA on the same SM fills the MUFU while this one waits):
 //   softmax j : read S_j into registers -> [s_consumed] -> row max -> exponentials in place -> P_j to TMEM -> [p_full]
 //   MMA warp  : S_{j+1} = Q K_{j+1}^T is issued at s_consumed(j), i.e. it runs underneath the exponentials of
@@ -92,6 +214,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int n_kv = (p.L + kTk - 1) / kTk;
+  const int kv_valid_tail = p.L - (n_kv - 1) * kTk;   // keys in the last KV tile (1..128)
+  const int nt16 = (kv_valid_tail + 15) & ~15;        // ... rounded up to the MMA's N / K granularity
   long long* tl = (g_fwd_timeline && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
                    (warp == 5 || warp == 0))
                       ? g_fwd_timeline
@@ -142,6 +266,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
     const uint64_t dq = make_desc_kmajor(smem_u32(sQ));
     const uint64_t dk0 = make_desc_kmajor(smem_u32(sK));
     const uint64_t dv0 = make_desc_mnmajor(smem_u32(sV), 64 * 128);
+    // ragged last KV tile: S only for the first nt16 keys (N of the MMA), PV only over those nt16 / 16 K steps
+    const uint32_t idesc_s_tail = make_idesc_bf16(kTq, nt16, 0, 0);
     mbar_wait(q_full, 0);
     for (int j = -1; j < n_kv; ++j) {
       if (j + 1 < n_kv) {  // S_{j+1}: as soon as S_j sits in the softmax threads' registers
@@ -150,9 +276,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
         mbar_wait(&k_full[st1], ((j + 1) / kFwdStages) & 1);
         tc_fence_after();
         const uint64_t dk = dk0 + static_cast<uint64_t>(st1 * (kTk * kHd * 2 >> 4));
+        const uint32_t id = (j + 1 == n_kv - 1) ? idesc_s_tail : idesc_s;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          for (int k = 0; k < kHd / 16; ++k) umma_ss(tS, dq + 2 * k, dk + 2 * k, id, k ? 1u : 0u);
           umma_commit(s_full);
           umma_commit(&k_empty[st1]);
         }
@@ -165,10 +292,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
         mbar_wait(&v_full[st], (j / kFwdStages) & 1);
         tc_fence_after();
         const uint64_t dv = dv0 + static_cast<uint64_t>(st * (kTk * kHd * 2 >> 4));
+        const int ksteps = (j == n_kv - 1) ? nt16 / 16 : kTk / 16;
         if (elect_one()) {
           umma_ts(tO, tP, dv, idesc_pv, j ? 1u : 0u);
 #pragma unroll
-          for (int k = 1; k < kTk / 16; ++k) umma_ts(tO, tP + 8 * k, dv + 128 * k, idesc_pv, 1u);
+          for (int k = 1; k < kTk / 16; ++k)
+            if (k < ksteps) umma_ts(tO, tP + 8 * k, dv + 128 * k, idesc_pv, 1u);
           umma_commit(p_free);
           umma_commit(&v_empty[st]);
         }
@@ -185,118 +314,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
     const int row = q0 + warp * 32 + lane;
     float m = -INFINITY, l = 0.f;
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int kv0 = j * kTk;
-      const bool tail = kv0 + kTk > p.L;
-      TLF(1, j, 0);
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      TLF(1, j, 1);
-      uint32_t sr[128];
-      tmem_ld32(tS + lane_base, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
-      tmem_ld32(tS + lane_base + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
-      tmem_ld32(tS + lane_base + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
-      tmem_ld32(tS + lane_base + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_consumed);  // S_{j+1} may overwrite tS
-      TLF(1, j, 2);
-      if (tail) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (kv0 + i >= p.L) sr[i] = 0xff800000u;  // -inf
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      if constexpr (PK) {
-#pragma unroll
-        for (int i = 0; i < 128; i += 8) {
-          mx0 = fmax3(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
-          mx2 = fmax3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
-          mx3 = fmax3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
-        }
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.sl2;
-      const bool grow = mx > m + 8.0f;  // first tile: m = -inf -> true
-      bool pv_done = j == 0;            // has this thread observed the completion of PV_{j-1} ?
-      if (__any_sync(0xffffffffu, grow)) {
-        const float alpha = grow ? fast_exp2(m - mx) : 1.0f;  // exp2(-inf) = 0 on the first tile
-        if (grow) {
-          m = mx;
-          l *= alpha;
-        }
-        if (j > 0) {  // rescale the O accumulator in TMEM (warp-collective; lanes that did not grow use 1)
-          mbar_wait(p_free, (j - 1) & 1);
-          tc_fence_after();
-          pv_done = true;
-#pragma unroll
-          for (int c = 0; c < kHd / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tO + lane_base + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tO + lane_base + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
-            tmem_st16(tO + lane_base + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
-          }
-        }
-      }
-      TLF(1, j, 3);
-      // exponentials in place (S_{j+1} and PV_{j-1} run on the tensor pipe meanwhile)
-      if constexpr (PK) {
-        const uint64_t sl2x2 = pack_f32x2(p.sl2, p.sl2), negm = pack_f32x2(-m, -m);
-        uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = sum_a;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sl2x2, negm);
-          uint64_t pr;
-          float p0, p1;
-          if ((PM >> (i & 7)) & 1) {
-            pr = exp2_poly_f32x2(x);
-            unpack_f32x2(pr, p0, p1);
-          } else {
-            unpack_f32x2(x, p0, p1);
-            p0 = fast_exp2(p0);
-            p1 = fast_exp2(p1);
-            pr = pack_f32x2(p0, p1);
-          }
-          if (i & 1) sum_b = add_f32x2(sum_b, pr); else sum_a = add_f32x2(sum_a, pr);
-          sr[i] = pack_bf16(p0, p1);
-        }
-        float s0, s1;
-        unpack_f32x2(add_f32x2(sum_a, sum_b), s0, s1);
-        l += s0 + s1;
-      } else {
-        float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 128; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.sl2, -m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.sl2, -m));
-          sum0 += p0;
-          sum1 += p1;
-          sr[i >> 1] = pack_bf16(p0, p1);
-        }
-        l += sum0 + sum1;
-      }
-      TLF(1, j, 4);
-      if (!pv_done) {  // PV_{j-1} has finished reading P_{j-1}
-        mbar_wait(p_free, (j - 1) & 1);
-        tc_fence_after();
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st16(tP + lane_base + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&sr[c * 16]));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_full);
-      TLF(1, j, 5);
+    const FwdBars fb{s_full, s_consumed, p_full, p_free};
+    for (int j = 0; j < n_kv - 1; ++j)
+      fwd_softmax_tile<4, PK, PM>(j, p.L, fb, tS, tP, tO, lane_base, p.sl2, m, l, tl);
+    switch ((kv_valid_tail + 31) >> 5) {  // the last tile, by the number of 32-key chunks that hold keys
+      case 1: fwd_softmax_tile<1, PK, PM>(n_kv - 1, p.L, fb, tS, tP, tO, lane_base, p.sl2, m, l, tl); break;
+      case 2: fwd_softmax_tile<2, PK, PM>(n_kv - 1, p.L, fb, tS, tP, tO, lane_base, p.sl2, m, l, tl); break;
+      case 3: fwd_softmax_tile<3, PK, PM>(n_kv - 1, p.L, fb, tS, tP, tO, lane_base, p.sl2, m, l, tl); break;
+      default: fwd_softmax_tile<4, PK, PM>(n_kv - 1, p.L, fb, tS, tP, tO, lane_base, p.sl2, m, l, tl); break;
     }
 
     mbar_wait(p_free, (n_kv - 1) & 1);

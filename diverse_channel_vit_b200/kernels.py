@@ -59,6 +59,11 @@ def gemm_nn(a, b, epilogue=EPI_BIAS, out=None, aux=None):
     return out
 
 
+def delta_ws(B, H, L, device, zero=False):
+    """The `delta` workspace of the attention backward: fp32 [B, H, Lp]."""
+    return (torch.zeros if zero else torch.empty)((B, H, lpad(L)), device=device, dtype=torch.float32)
+
+
 def gemm_nn_delta(dy, w, o, B, L):
     """dO = dy[M,K] @ w[K,N] (bf16) and delta[B, N/64, Lp] = per-head rowsum(dO * o); M = B*L."""
     _req(dy, torch.bfloat16, "dy"); _req(w, torch.bfloat16, "w"); _req(o, torch.bfloat16, "o")
@@ -66,7 +71,7 @@ def gemm_nn_delta(dy, w, o, B, L):
     N = w.shape[1]
     assert M == B * L and o.shape == (M, N) and o.is_contiguous()
     d_o = torch.empty((M, N), device=dy.device, dtype=torch.bfloat16)
-    delta = torch.zeros((B, N // 64, lpad(L)), device=dy.device, dtype=torch.float32)
+    delta = delta_ws(B, N // 64, L, dy.device, zero=True)
     check(_lib.lib().dcv_gemm_nn_delta(ptr(dy), dy.stride(0), ptr(w), w.stride(0), M, N, K, ptr(d_o), ptr(o), ptr(delta),
                                        L, stream_ptr()), "dcv_gemm_nn_delta")
     return d_o, delta
@@ -116,7 +121,7 @@ def attn_bwd(qkv, o, do, lse2, B, L, H, scale=None, dqkv=None, delta=None, dq_ac
         dqkv = torch.empty((B * L, 3 * D), device=dev, dtype=torch.bfloat16)
     if delta is None:
         assert not delta_ready
-        delta = torch.empty((B, H, lpad(L)), device=dev, dtype=torch.float32)
+        delta = delta_ws(B, H, L, dev)
     if dq_acc is None:
         dq_acc = torch.empty((B, H, L, 64), device=dev, dtype=torch.float32)
     scale = 64 ** -0.5 if scale is None else scale

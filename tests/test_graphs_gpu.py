@@ -75,7 +75,9 @@ def test_graphed_steps_equal_eager_steps(sample):
             assert torch.equal(pg, pe_)  # unused on a classifier-head model: untouched in both
         else:
             w0 = weights[k].cuda()
-            assert rel_l2(pg, pe_) < 1e-2, k
+            # matrices: 1e-2; vectors (biases, LayerNorm) start at or near 0 / 1 and are mostly "update" after 14 AdamW
+            # steps, whose normalised first steps amplify last-bit differences of the atomics' summation order
+            assert rel_l2(pg, pe_) < (1e-2 if pg.dim() >= 2 else 3e-2), k
             if k.endswith("weight") and pg.dim() == 2:  # the UPDATES agree, not just the (barely moved) parameters
                 assert torch.nn.functional.cosine_similarity((pg - w0).flatten(), (pe_ - w0).flatten(), dim=0) > 0.9, k
     assert step.opt.device_state()["num_updates"] == n_steps

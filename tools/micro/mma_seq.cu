@@ -7,13 +7,21 @@
 using namespace dcv;
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 1) seq_kernel(long long* out, int iters, int stage_stride) {
+__global__ void __launch_bounds__(128, 1) seq_kernel(long long* out, int iters, int stage_stride, int random_fill) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar[8];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) {
+    uint32_t v = 0x3c003c00u;
+    if (random_fill) {  // random signs / mantissas, exponents around 1.0 (what real activations look like to the datapath)
+      uint32_t h = (i + 1) * 2654435761u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      v = (h & 0x807f807fu) | 0x3f003f00u | ((h >> 3) & 0x00800080u);
+    }
+    reinterpret_cast<uint32_t*>(smem)[i] = v;
+  }
   if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(&slot, 512);
   fence_proxy_async_smem();
@@ -64,13 +72,13 @@ __global__ void __launch_bounds__(128, 1) seq_kernel(long long* out, int iters, 
 }
 
 template <int MODE>
-void run(const char* name) {
+void run(const char* name, int random_fill = 0) {
   long long* d; cudaMalloc(&d, 64);
   const int smem = 160 * 1024 + 2048;
   cudaFuncSetAttribute(seq_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int iters = 200;
-  seq_kernel<MODE><<<148, 128, smem>>>(d, iters, 0);
-  seq_kernel<MODE><<<148, 128, smem>>>(d, iters, 0);
+  const int iters = 2000;
+  seq_kernel<MODE><<<148, 128, smem>>>(d, iters, 0, random_fill);
+  seq_kernel<MODE><<<148, 128, smem>>>(d, iters, 0, random_fill);
   cudaDeviceSynchronize();
   long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   printf("%-44s issue %.0f cyc/pair, complete %.0f cyc/pair (32 MMAs; calibrated sum 1640)  %s\n", name,
@@ -82,5 +90,8 @@ int main() {
   run<0>("sequence, no commits");
   run<1>("sequence, commit after each group");
   run<2>("sequence, + wait for completion every pair");
+  run<0>("RANDOM data: sequence, no commits", 1);
+  run<1>("RANDOM data: commit after each group", 1);
+  run<2>("RANDOM data: + wait every pair", 1);
   return 0;
 }

@@ -90,7 +90,7 @@ if okb:
         D = H * 64
         qkv = torch.randn(B * L, 3 * D, device=dev).bfloat16(); do = torch.randn(B * L, D, device=dev).bfloat16()
         o, lse = K.attn_fwd(qkv, B, L, H)
-        dqkv = torch.empty_like(qkv); delta = torch.empty(B, H, K.lpad(L), device=dev); acc = torch.empty(B, H, L, 64, device=dev)
+        dqkv = torch.empty_like(qkv); delta = K.delta_ws(B, H, L, dev); acc = torch.empty(B, H, L, 64, device=dev)
         ms = bench(lambda: K.attn_bwd(qkv, o, do, lse, B, L, H, dqkv=dqkv, delta=delta, dq_acc=acc))
         fl = 8.0 * B * H * L * L * 64
         print(f"attn bwd B{B} L{L}: {ms*1e3:.1f} us = {fl/ms/1e9:.1f} TFLOP/s (algorithmic 8*L^2*D)", flush=True)
