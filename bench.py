@@ -549,8 +549,7 @@ def ours(args, wname):
     gemm_tf = 3.0 * fl["gemm_nt"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world)
         return
 
     # ---- attention kernels next to the library kernel on the same box (torch SDPA, cuDNN backend), at this
@@ -626,8 +625,20 @@ def ours(args, wname):
         fwd += nb * (2.0 * (Lc - 1) * w["patch"] ** 2 * D + depth * (24.0 * Lc * D * D + 4.0 * Lc * Lc * D) + 2.0 * D * w["classes"])
     line["full_channels"]["model_tflops"] = 3.0 * fwd * world / (ms_full / kf * 1e-3) / 1e12
     print(json.dumps(line), flush=True)
+    _leave(world)
+
+
+def _leave(world: int) -> None:
+    """End of a multi-rank run.  The NCCL communicator is NOT torn down: destroy_process_group() blocks forever while
+    CUDA graphs that captured collectives of that communicator are alive (seen at N = 2: the JSON line was out, the
+    process never exited), and there is nothing to save -- flush and leave."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def attention_vs_sdpa(B: int, L: int, H: int):
@@ -774,8 +785,7 @@ def eval_mode(args, wname):
                 "gpu_launches": int(n_launch), "clocks": clocks,
                 "model_tflops": fwd * world / (ms / K * 1e-3) / 1e12}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _leave(world)
 
 
 def main():

@@ -207,6 +207,16 @@ class FusedAdamW:
                 check(lib.dcv_sumsq_f32(c_void_p(g.data_ptr() + 4 * a), c_longlong(b - a), c_void_p(self._clip.data_ptr()), st),
                       "dcv_sumsq_f32")
             clip_ptr = c_void_p(self._clip.data_ptr())
+            if getattr(m, "grad_allreduce", False):
+                # The sum of squares is accumulated with fp32 atomics: its last bit depends on the order the CTAs finish
+                # in, so two replicas holding bit-identical averaged gradients can get clip factors one ulp apart and
+                # drift away from each other for good (measured: 138 of 154 parameters off by an ulp after 8 steps on
+                # 2 GPUs).  One 4-byte MAX all-reduce makes every rank use the same value (DDP keeps replicas
+                # bit-identical, reference trainer.py:1185).
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized():
+                    dist.all_reduce(self._clip[0:1], op=dist.ReduceOp.MAX, group=getattr(m, "_pg", None))
         if self.device_schedule:
             if self._state is None or self._state.device != dev:
                 self._state = torch.zeros(8, dtype=torch.float32, device=dev)
