@@ -1,6 +1,7 @@
 // extern "C" surface of libdcvit.so (declared in include/dcvit.h) plus the host
 // utilities shared by all launchers.
 #include <atomic>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -53,6 +54,20 @@ ProfScope::~ProfScope() {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (slot < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot].b, st);
 }
+
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    // off unless DCV_PDL=1: measured with both sets of graphs in one process (tools/pdl_ab.py, JUMP-CP B=32) the step is
+    // 4.6 % faster at C' = 1, unchanged at C' = 2 and 2-6 % SLOWER from C' = 4 up
+    const char* e = getenv("DCV_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+void debug_set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 int num_sms() {
   static std::atomic<int> sms_by_dev[64];
@@ -382,6 +397,8 @@ void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes) { debug_set_tn_desc(lbo
 void dcv_debug_set_nt_cluster(int cm) { debug_set_nt_cluster(cm); }
 
 int dcv_debug_attn_timeline(long long* buf) { return debug_attn_timeline(buf); }
+
+void dcv_debug_set_pdl(int on) { debug_set_pdl(on); }
 
 void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode) {
   if (fwd_mode >= 0) debug_set_attn_fwd_mode(fwd_mode);

@@ -221,6 +221,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
                       ? g_fwd_timeline
                       : nullptr;
 
+  pdl_launch_dependents();
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     mbar_init(q_full, 1);
@@ -242,6 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnFwdParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
+  pdl_wait();  // qkv (the previous GEMM's output) is complete and visible
 
   if (warp == 4) {
     if (lane == 0) {
@@ -385,8 +387,7 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
   const int all_tiles = (L + kTq - 1) / kTq;
   dim3 grid(q_tiles > 0 && q_tiles < all_tiles ? q_tiles : all_tiles, H, B);
   ProfScope prof(PT_ATTN_FWD, st);
-  kern<<<grid, 192, kFwdSmem, st>>>(map, p);
-  DCV_CUDA(cudaGetLastError());
+  DCV_CUDA(launch_pdl(kern, grid, dim3(192), kFwdSmem, st, map, p));
   count_launch();
   return 0;
 }

@@ -242,6 +242,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
                       ? g_attn_timeline
                       : nullptr;
 
+  pdl_launch_dependents();
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
@@ -276,6 +277,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   // P^T (bf16) and the dQ accumulator time-share columns [384,448); K and V sit in TMEM as A operands of S^T / dP^T
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384, tP = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
+  pdl_wait();  // dO / delta (projection dgrad) and the cleared dQ accumulator are complete and visible
 
   if (warp >= kWarpTma && warp < kWarpDrain0) {
     setmaxnreg_dec<40>();
@@ -588,6 +590,8 @@ constexpr int kFinRows = 128;
 __global__ void __launch_bounds__(256)
 attn_bwd_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
                        int B, int L, int H, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float part[8][kHd];
   const int bh = blockIdx.x;
   const int bb = bh / H, hh = bh - bb * H;
@@ -693,14 +697,12 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
   dim3 grid((L + kTk - 1) / kTk, H, B);
   {
     ProfScope prof(PT_ATTN_BWD, st);
-    kern<<<grid, kBwdThreads, kBwdSmem, st>>>(map_qkv, map_do, map_dq, p);
-    DCV_CUDA(cudaGetLastError());
+    DCV_CUDA(launch_pdl(kern, grid, dim3(kBwdThreads), kBwdSmem, st, map_qkv, map_do, map_dq, p));
   }
   {
     ProfScope prof(PT_ATTN_BWD_FIN, st);
-    attn_bwd_finish_kernel<<<dim3(B * H, (L + kFinRows - 1) / kFinRows), 256, 0, st>>>(
-        dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias_qkv, B, L, H, scale);
-    DCV_CUDA(cudaGetLastError());
+    DCV_CUDA(launch_pdl(attn_bwd_finish_kernel, dim3(B * H, (L + kFinRows - 1) / kFinRows), dim3(256), 0, st, dq_acc,
+                        reinterpret_cast<__nv_bfloat16*>(dqkv), dbias_qkv, B, L, H, scale));
   }
   count_launch(delta_ready ? 2 : 3);
   return 0;

@@ -19,6 +19,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still running.  pdl_launch_dependents(): this CTA no longer
+// objects to the NEXT kernel's CTAs being scheduled (they take SM slots as ours drain); pdl_wait(): blocks until the
+// PREVIOUS kernel has completed and its global writes are visible -- everything before it (barrier init, TMEM
+// allocation, tensor-map prefetch) overlaps the predecessor's tail.  Both are no-ops in a kernel launched without the
+// attribute.  Every kernel launched through launch_pdl() (host.h) must execute pdl_wait() before its first access to
+// global memory, on every path.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -138,6 +138,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     n0 = (ct % n_tiles) * BN;
   };
   constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CM) - 1);
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -169,6 +170,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();  // the previous kernel's outputs (our operands, residual, gradient accumulators) are complete and visible
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -623,6 +625,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int mb_begin = split * mb_per;
   const int mb_end = min(total_mb, mb_begin + mb_per);
   const int num_mb = max(0, mb_end - mb_begin);
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -641,6 +644,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();
 
   if (num_mb > 0) {
     if (warp == 0) {
@@ -765,13 +769,22 @@ static int launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmNtP
   cfg.blockDim = dim3(kNtThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CM;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CM > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CM;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CM > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   DCV_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, em.out, em.out2, em.in, p));
   count_launch();
   return 0;
@@ -905,8 +918,7 @@ static int launch_tn(const CUtensorMap& ma, const CUtensorMap& mb, GemmTnParams 
   p.sbo = g_tn_sbo ? g_tn_sbo : 1024;
   CUtensorMap mc;
   if (int e = make_tmap_2d(&mc, p.C, true, (uint64_t)p.Kout, (uint64_t)p.Nout, (uint64_t)p.ldc * 4, 32, kBM)) return e;
-  kern<<<tiles * splits, 256, Cfg::kSmemBytes, st>>>(ma, mb, mc, p);
-  DCV_CUDA(cudaGetLastError());
+  DCV_CUDA(launch_pdl(kern, dim3(tiles * splits), dim3(256), Cfg::kSmemBytes, st, ma, mb, mc, p));
   count_launch();
   return 0;
 }

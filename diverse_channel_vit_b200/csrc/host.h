@@ -100,6 +100,25 @@ int debug_attn_timeline(long long* buf);
 void debug_set_attn_fwd_mode(int m);
 void debug_set_attn_bwd_mode(int m);
 
+// ---- programmatic dependent launch ----
+// Opt-in: DCV_PDL=1 in the environment (read once) or dcv_debug_set_pdl(1); otherwise plain stream ordering.
+bool pdl_enabled();
+void debug_set_pdl(int on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- rowops.cu ----
 int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D,
            float eps, cudaStream_t st);

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(kRowWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int M, int D,
               float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 2;
   float4 g[NV], bt[NV];
@@ -118,6 +120,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
               const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dxsum, int M, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [kRowWarps][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 2;
@@ -425,10 +429,10 @@ int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float
   const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 8);
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   switch (nv_for(D)) {
-    case 1: ln_fwd_kernel<1><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
-    case 2: ln_fwd_kernel<2><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
-    case 3: ln_fwd_kernel<3><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
-    case 6: ln_fwd_kernel<6><<<blocks, kRowWarps * 32, 0, st>>>(x, gamma, beta, yb, mean, rstd, M, D, eps); break;
+    case 1: DCV_CUDA(launch_pdl(ln_fwd_kernel<1>, dim3(blocks), dim3(kRowWarps * 32), 0, st, x, gamma, beta, yb, mean, rstd, M, D, eps)); break;
+    case 2: DCV_CUDA(launch_pdl(ln_fwd_kernel<2>, dim3(blocks), dim3(kRowWarps * 32), 0, st, x, gamma, beta, yb, mean, rstd, M, D, eps)); break;
+    case 3: DCV_CUDA(launch_pdl(ln_fwd_kernel<3>, dim3(blocks), dim3(kRowWarps * 32), 0, st, x, gamma, beta, yb, mean, rstd, M, D, eps)); break;
+    case 6: DCV_CUDA(launch_pdl(ln_fwd_kernel<6>, dim3(blocks), dim3(kRowWarps * 32), 0, st, x, gamma, beta, yb, mean, rstd, M, D, eps)); break;
     default: return set_error(DCV_ERR_UNSUPPORTED, "ln_fwd: D=%d not instantiated (128/256/384/768 classes)", D);
   }
   DCV_CUDA(cudaGetLastError());
@@ -446,8 +450,8 @@ int ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd,
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
 #define LNB(NV)                                                                                                  \
-  ln_bwd_kernel<NV><<<blocks, kRowWarps * 32, smem, st>>>(dyb, x, mean, rstd, gamma, dres, dxb, dgamma, dbeta, \
-                                                           dxsum, M, D)
+  DCV_CUDA(launch_pdl(ln_bwd_kernel<NV>, dim3(blocks), dim3(kRowWarps * 32), smem, st, dyb, x, mean, rstd, gamma, dres, \
+                      dxb, dgamma, dbeta, dxsum, M, D))
   switch (nv_for(D)) {
     case 1: LNB(1); break;
     case 2: LNB(2); break;

@@ -318,6 +318,12 @@ int dcv_debug_attn_timeline(long long* buf);
  * A negative value leaves that kernel's mode unchanged. */
 void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode);
 
+/* debug / A-B timing: programmatic dependent launch of the GEMM, LayerNorm and attention kernels (off by default,
+ * DCV_PDL=1 in the environment switches it on): each of them may become resident while its predecessor in the stream
+ * drains and waits (griddepcontrol.wait) for the predecessor's results before touching global memory.  Measured
+ * (tools/pdl_ab.py): faster only for the shortest sequences, slower from ~800 tokens up -- hence opt-in. */
+void dcv_debug_set_pdl(int on);
+
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);
 
