@@ -2,7 +2,8 @@
 //
 //   gemm_nt :  C[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)        -- both operands K-major
 //              forward Linear layers (reference models/vit.py:116,118,71-73) and their
-//              dgrad (dX = dY * W, run against a pre-transposed bf16 copy of W).
+//              dgrad (dX = dY * W: the same kernel with W[out,in] consumed directly as an MN-major B operand,
+//              template flag Bmn -- no transposed copy of W exists).
 //   gemm_tn :  C[N,K] += A[M,N]^T * B[M,K]                             -- both operands MN-major
 //              weight gradients dW = dY^T X, reduction over the B*L token rows, split-K.
 //
