@@ -408,6 +408,32 @@ def bicubic_pos_matrix(grid: int, w: int, h: int, patch: int) -> torch.Tensor:
     return out.permute(0, 2, 3, 1).reshape(-1, n_in).contiguous()
 
 
+def bicubic_pos_backward_matrix(grid: int, w: int, h: int, patch: int) -> Optional[torch.Tensor]:
+    """What the reference's BACKWARD applies to the gradient of the resampled positional grid -- which is not the
+    transpose of `bicubic_pos_matrix`: ATen's upsample_bicubic2d backward, reached through F.interpolate(scale_factor=...),
+    derives its sampling scale from the tensor sizes (out / in), not from the (w//P + 0.1)/grid the forward was given.
+    For every training shape (w//P == grid) that scale is 1 and the backward is the IDENTITY, while the forward matrix
+    has ~1.8 % off-diagonal mass: the true adjoint differs from what the reference trains with by 9 % on the patch rows
+    of d pos_embed (So2Sat shape, found with tools/grad_diag.py).  Parity means the reference's gradient, so this is the
+    matrix autograd itself applies, read out with one backward pass over one-hot output gradients.  Returns
+    [N_out, N_in] (d pos_in = M^T d pos_out), or None when it is the identity (no map in the backward)."""
+    n_in = grid * grid
+    w0, h0 = w // patch + 0.1, h // patch + 0.1
+    wo, ho = int(w0), int(h0)
+    n_out = wo * ho
+    with torch.enable_grad():
+        x = torch.zeros(1, n_out, grid, grid, dtype=torch.float32, requires_grad=True)
+        y = F.interpolate(x, scale_factor=(w0 / grid, h0 / grid), mode="bicubic")
+        gy = torch.zeros_like(y)
+        j = torch.arange(n_out)
+        gy[0, j, j // ho, j % ho] = 1.0
+        y.backward(gy)
+    m = x.grad[0].reshape(n_out, n_in).contiguous()
+    if n_out == n_in and torch.equal(m, torch.eye(n_in)):
+        return None
+    return m
+
+
 # ---------------------------------------------------------------------------------------------
 # flat parameter store
 # ---------------------------------------------------------------------------------------------
@@ -756,7 +782,17 @@ class DiChaViT(nn.Module):
         return dict(B=B, cs=cs, H=H, W=W, P=P, D=D, heads=heads, N=N, T=T, L=L, M=M, F=Fh, Lp=Lp, depth=depth,
                     arena=ar, keep=keep)
 
-    def _embed_structs(self, pl, base: int, scal: torch.Tensor, C_in: int, use_map: bool, device, call: dict):
+    def _pos_map_bwd(self, w: int, h: int, device) -> Optional[torch.Tensor]:
+        fe = self.feature_extractor
+        n = fe.pos_embed.shape[1] - 1
+        key = ("bwd", w, h, str(device))
+        if key not in self._pos_maps:
+            m = bicubic_pos_backward_matrix(int(math.sqrt(n)), w, h, fe.patch_size)
+            self._pos_maps[key] = m.to(device) if m is not None else None
+        return self._pos_maps[key]
+
+    def _embed_structs(self, pl, base: int, scal: torch.Tensor, C_in: int, use_map: bool, device, call: dict,
+                       backward: bool = False):
         fe = self.feature_extractor
         pe = fe.patch_embed
         cfg = self.cfg
@@ -770,7 +806,14 @@ class DiChaViT(nn.Module):
         ecfg = _EmbedCfg(l_tdl, l_cdl, float(cfg.gamma_s), float(cfg.gamma_d), float(pe.channel_scale),
                          int(bool(cfg.reverse_pos_pairs)), int(bool(cfg.use_square)), int(call["x_is_u8"]))
         has_prox = hasattr(pe, "channel_emb_proxies")
-        pos_map = self._pos_map(pl["W"], pl["H"], device) if use_map else None
+        # forward: the bicubic resample matrix; backward: what the reference's autograd applies instead of its transpose
+        # (bicubic_pos_backward_matrix; None = identity, the kernels then accumulate d pos_embed directly)
+        if not use_map:
+            pos_map = None
+        elif backward:
+            pos_map = self._pos_map_bwd(pl["W"], pl["H"], device)
+        else:
+            pos_map = self._pos_map(pl["W"], pl["H"], device)
         ce_ptr = call["ce_override"].data_ptr() if call["ce_override"] is not None else \
             self._fptr(pe.channel_embed.weight)
         ep = _EmbedParams(self._fptr(pe.proj.weight), self._fptr(pe.proj.bias), ce_ptr,
@@ -960,7 +1003,8 @@ class DiChaViT(nn.Module):
             if reducer:
                 reducer.ready(f"block{i}")
         call = state["call"]
-        dims, ecfg, ep, eacts, _ = self._embed_structs(pl, base, state["scal"], state["C_in"], state["use_map"], dev, call)
+        dims, ecfg, ep, eacts, _ = self._embed_structs(pl, base, state["scal"], state["C_in"], state["use_map"], dev, call,
+                                                       backward=True)
         has_prox = hasattr(pe, "channel_emb_proxies")
         # no channel-token gradient when the tokens are frozen (freeze_channel_emb) or were synthesised for unseen
         # channels (eval-time leave-one-out: gid indexes the synthesised matrix, not channel_embed.weight)
@@ -974,6 +1018,9 @@ class DiChaViT(nn.Module):
         check(lib.dcv_embed_bwd(byref(dims), byref(ecfg), byref(ep), c_void_p(state["gid"].data_ptr()), byref(eacts),
                                 byref(eg), byref(ews), c_void_p(wb + w["dres"]),
                                 c_void_p(d_extra.data_ptr()) if d_extra is not None else None, st), "dcv_embed_bwd")
+        if getattr(self, "_debug_keep_token_grad", False):  # diagnostics (tools/grad_diag.py): dLoss/d tokens, fp32 [B, L, D]
+            off = w["dres"]
+            self._last_token_grad = wbuf[off:off + M * D * 4].view(torch.float32).view(B, L, D).clone()
         if reducer:
             reducer.ready("embed", flush=True)
             reducer.finish()

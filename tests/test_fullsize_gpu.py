@@ -7,8 +7,8 @@ extra loss, and per parameter the gradient norm, sum and 16 sampled elements).
 Tolerances (north_star): rel-L2 <= 1e-2 on logits, <= 1e-3 on the scalar losses.  Parameter gradients: rel-L2 <= 1e-2
 per parameter on the three benched configurations -- tighter than what the reference's own bf16 path (torch.autocast on
 the same GPU) achieves against the same oracle (profiles/r2_grad_error_vs_amp.txt: worst 8.97e-3 / 2.42e-2 / 9.42e-3
-here against 1.01e-2 / 1.85e-2 / 1.09e-2 under autocast) -- with two named exceptions: `pos_embed` on the So2Sat-shaped
-model (POS_EMBED_TOL) and the sampled-channel draw (SAMPLED_TOL)."""
+here against 1.01e-2 / 1.85e-2 / 1.09e-2 under autocast; after the positional-embedding backward fix below: 8.75e-3 /
+9.09e-3 / 8.97e-3) -- with one named exception: the sampled-channel draw (SAMPLED_TOL)."""
 import numpy as np
 import pytest
 import torch
@@ -20,11 +20,11 @@ pytestmark = pytest.mark.gpu
 ACT_TOL = 1e-2
 LOSS_TOL = 1e-3
 GRAD_TOL = 1e-2
-# pos_embed's gradient is the sum over batch x channels (8 x 18 = 144 token gradients per element on So2Sat) of
-# nearly cancelling terms: |sum| ~ sqrt(n) * |term| while bf16 rounding noise of the upstream GEMM outputs adds up the
-# same way, and any error component that is coherent across tokens adds up linearly.  Measured 2.4e-2 (the reference's
-# autocast path: 1.3e-2); every other parameter of that model is <= 9.2e-3.
-POS_EMBED_TOL = 3e-2
+# pos_embed used to be the exception here (2.4e-2 on the So2Sat model, explained in round 1 as a cancelling sum).  It
+# was a parity bug: the kernels applied the transpose of the bicubic resample matrix, the reference's autograd does
+# not (ATen's bicubic backward derives its scale from the tensor sizes, i.e. the identity at every training shape) --
+# 9 % on the patch rows of d pos_embed.  Fixed in dichavit.bicubic_pos_backward_matrix; pos_embed is now 7-8e-3.
+POS_EMBED_TOL = GRAD_TOL
 # C' = 3 draw (L = 589): fewer tokens average the bf16 rounding noise of each gradient element, and the fp32 atomics of
 # the bias / LayerNorm reductions make the last digits run-dependent: block-0 LayerNorm gains measured 9.7e-3 .. 1.03e-2
 # over repeated runs (the reference's autocast path: 1.06e-2 on the same parameter, 1.12e-2 worst).
@@ -82,7 +82,7 @@ def test_full_size_jumpcp_vit_s16_all_channels():
 
 def test_full_size_jumpcp_vit_s16_sampled_channels():
     """configs[2] with one sampled draw in sampled (unsorted) order: C' = 3, L = 589, bicubic pos resample."""
-    _run("full_c3", indices=[5, 0, 3], golden=False, pos_tol=1.5e-2, grad_tol=SAMPLED_TOL)
+    _run("full_c3", indices=[5, 0, 3], golden=False, pos_tol=SAMPLED_TOL, grad_tol=SAMPLED_TOL)
 
 
 def test_full_size_so2sat_vit_s8_all_blocks():

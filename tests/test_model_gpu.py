@@ -17,7 +17,11 @@ pytestmark = pytest.mark.gpu
 
 ACT_TOL = 1e-2
 LOSS_TOL = 1e-3
-GRAD_TOL = 3e-2
+# small golden models (L <= 129 tokens, few tokens to average the bf16 noise of each gradient element over): worst
+# parameter 9.3e-3 ... 1.09e-2 over the cases (autocast: 1.8e-2) once the positional-embedding backward matches the
+# reference's autograd (2.4e-2 before: dichavit.bicubic_pos_backward_matrix); 1e-2 at the benched sizes
+# (tests/test_fullsize_gpu.py)
+GRAD_TOL = 1.5e-2
 
 
 def _oracle(name, indices=None):

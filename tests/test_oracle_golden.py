@@ -150,3 +150,34 @@ def test_leave_one_out_matches_reference():
         pe.leave_one_out_tokens("test", "train", "dynamic_input_corr_1")
     with pytest.raises(ValueError):
         pe.leave_one_out_tokens("test", "train", "nonsense")
+
+
+def test_bicubic_backward_is_what_autograd_applies_not_the_adjoint():
+    """reference models/dichavit.py:531-549: the positional grid goes through F.interpolate(scale_factor=(w0+0.1)/grid,
+    mode="bicubic").  ATen's backward of that call is NOT the transpose of its forward: it derives the sampling scale
+    from the tensor sizes.  At every training shape (w // P == grid) the forward matrix is off the identity by ~2-3 %
+    while the backward IS the identity -- the drop-in has to reproduce that, not the exact adjoint."""
+    import torch.nn.functional as F
+
+    from diverse_channel_vit_b200.dichavit import bicubic_pos_backward_matrix, bicubic_pos_matrix
+
+    for grid, w, patch in ((4, 32, 8), (14, 224, 16), (2, 32, 16)):
+        fwd = bicubic_pos_matrix(grid, w, w, patch)
+        assert (fwd - torch.eye(grid * grid)).abs().max() > 5e-3          # the forward resamples ...
+        assert bicubic_pos_backward_matrix(grid, w, w, patch) is None      # ... the backward does not
+        x = torch.randn(1, 3, grid, grid, dtype=torch.float64, requires_grad=True)
+        y = F.interpolate(x, scale_factor=((w // patch + 0.1) / grid,) * 2, mode="bicubic")
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        assert torch.equal(x.grad, gy)
+    # another image size (evaluation with a gradient): whatever autograd applies is what the matrix holds
+    grid, w, patch = 4, 64, 8
+    mb = bicubic_pos_backward_matrix(grid, w, w, patch)
+    assert mb is not None and mb.shape == (64, 16)
+    x = torch.randn(1, 5, grid, grid, requires_grad=True)
+    y = F.interpolate(x, scale_factor=((w // patch + 0.1) / grid,) * 2, mode="bicubic")
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    want = x.grad[0].reshape(5, 16).t()                                    # [N_in, D]
+    got = mb.t() @ gy[0].reshape(5, 64).t()
+    assert torch.allclose(got, want, atol=1e-5)
