@@ -232,6 +232,24 @@ int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
   return 0;
 }
 
+int make_tmap_f32_5d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t d4,
+                     uint64_t s1, uint64_t s2, uint64_t s3, uint64_t s4, uint32_t b0, uint32_t b1, uint32_t b2,
+                     uint32_t b3, uint32_t b4) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((s1 | s2 | s3 | s4) & 15))
+    return set_error(DCV_ERR_UNSUPPORTED, "TMA operand must be 16-byte aligned");
+  cuuint64_t dims[5] = {d0, d1, d2, d3, d4};
+  cuuint64_t strides[4] = {s1, s2, s3, s4};
+  cuuint32_t box[5] = {b0, b1, b2, b3, b4};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DCV_ERR_CUDA, "cuTensorMapEncodeTiled(5d f32) failed: %d", (int)r);
+  return 0;
+}
+
 }  // namespace dcv
 
 using namespace dcv;
@@ -399,6 +417,7 @@ void dcv_debug_set_nt_cluster(int cm) { debug_set_nt_cluster(cm); }
 int dcv_debug_attn_timeline(long long* buf) { return debug_attn_timeline(buf); }
 
 void dcv_debug_set_pdl(int on) { debug_set_pdl(on); }
+void dcv_debug_set_embed_fused(int on) { debug_set_embed_fused(on); }
 
 void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode) {
   if (fwd_mode >= 0) debug_set_attn_fwd_mode(fwd_mode);

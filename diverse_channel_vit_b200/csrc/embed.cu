@@ -807,12 +807,20 @@ int tdl_fwd(const float* tokens, const float* addend, const float* bias, float* 
     cfg.numAttrs = split > 1 ? 1 : 0;
     DCV_NV_SWITCH(D, DCV_CUDA(cudaLaunchKernelEx(&cfg, tdl_sum_kernel<NV>, tokens, addend, bias, S, Q, rnorm, Cs, N, D, split)));
   }
+  count_launch();
+  return tdl_finish(S, Q, S_all, loss_b, coef_pos, coef_neg, tdl_out, B, Cs, N, D, gamma_s, gamma_d, reverse_pos_pairs,
+                    use_square, st);
+}
+
+int tdl_finish(float* S, float* Q, float* S_all, float* loss_b, float* coef_pos, float* coef_neg, float* tdl_out, int B,
+               int Cs, int N, int D, float gamma_s, float gamma_d, int reverse_pos_pairs, int use_square, cudaStream_t st) {
+  ProfScope prof(PT_TDL, st);
   TdlFlags f{gamma_s, gamma_d, reverse_pos_pairs, use_square};
   tdl_pair_kernel<<<B, 128, 0, st>>>(S, Q, S_all, loss_b, coef_pos, coef_neg, B, Cs, N, D, f);
   DCV_CUDA(cudaGetLastError());
   reduce_sum_kernel<<<1, 256, 0, st>>>(loss_b, B, 1.0f / static_cast<float>(B), tdl_out);
   DCV_CUDA(cudaGetLastError());
-  count_launch(3);
+  count_launch(2);
   return 0;
 }
 

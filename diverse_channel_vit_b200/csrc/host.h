@@ -56,6 +56,10 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t inner, u
 // 3-D fp32 tensor (used for the TMA reduce-add of the attention dQ accumulator)
 int make_tmap_f32_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+// 5-D fp32 map without swizzle (image strips of the fused patch embedding); not cached
+int make_tmap_f32_5d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t d4,
+                     uint64_t s1, uint64_t s2, uint64_t s3, uint64_t s4, uint32_t b0, uint32_t b1, uint32_t b2,
+                     uint32_t b3, uint32_t b4);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (kernel, device): applied once for each pair, thread-safe
 int ensure_smem_attr(const void* kernel, int bytes);
@@ -160,6 +164,16 @@ int cls_ln_fwd(const float* x, long long row_stride, const float* gamma, const f
 int cls_ln_bwd(const float* dfeat, const float* x, long long row_stride, const float* mean, const float* rstd,
                const float* gamma, float* dres, void* dres_bf16, float* dgamma, float* dbeta, float* dxsum, int B,
                int D, cudaStream_t st);
+
+// ---- embed_fused.cu ----
+bool embed_fused_ok(const dcv_embed_dims& d, int x_is_u8);
+void debug_set_embed_fused(int on);
+int embed_fused_fwd(const dcv_embed_dims& d, const void* x, const int* idx, const void* wsplit, const float* bias,
+                    const float* addend, float* tokens, void* patches, float* S, float* Q, float* rnorm, int tdl_on,
+                    cudaStream_t st);
+// the two small kernels that turn S / Q into the TDL scalar and its backward coefficients (second half of tdl_fwd)
+int tdl_finish(float* S, float* Q, float* S_all, float* loss_b, float* coef_pos, float* coef_neg, float* tdl_out, int B,
+               int Cs, int N, int D, float gamma_s, float gamma_d, int reverse_pos_pairs, int use_square, cudaStream_t st);
 
 // ---- model.cu (stage orchestration behind dcv_block_* / dcv_embed_* / dcv_head_*) ----
 int block_fwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts& a, cudaStream_t st);

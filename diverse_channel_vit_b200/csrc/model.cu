@@ -133,8 +133,10 @@ int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed
   if (!x || !gid || !a.patches || !a.wsplit || !a.addend || !a.tokens || !a.extra)
     return set_error(DCV_ERR_INVALID, "embed_fwd: null pointer");
   const int N = (d.H / d.P) * (d.W / d.P), T = d.Cs * N, K = d.P * d.P, D = d.D;
-  // DCS gather + unfold (dichavit.py:210, :377)
-  DCV_TRY(im2col_gather(x, cfg.x_is_u8, p.pix_mean, p.pix_inv_std, idx, a.patches, d.B, d.C, d.Cs, d.H, d.W, d.P, st));
+  const bool fused = embed_fused_ok(d, cfg.x_is_u8);
+  // DCS gather + unfold (dichavit.py:210, :377) -- inside the fused kernel when the shape allows it
+  if (!fused)
+    DCV_TRY(im2col_gather(x, cfg.x_is_u8, p.pix_mean, p.pix_inv_std, idx, a.patches, d.B, d.C, d.Cs, d.H, d.W, d.P, st));
   DCV_TRY(split_weight(p.proj_w, a.wsplit, D, K, st));
   // positional embedding of the patches: raw or bicubic-resampled (dichavit.py:529-552)
   const float* pos_patch = p.pos + D;
@@ -145,12 +147,22 @@ int embed_fwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed
   DCV_TRY(embed_addend(p.proj_b, p.chan_embed, gid, pos_patch, p.cls, p.pos, a.addend, a.tokens, d.B, d.Cs, N, D, st));
   // tokens[b, 1 + t, :] = patches * W^T + addend[t]   (conv + bias + channel token + pos, :377,:409-411,:565)
   // (3K-wide split-precision operands: [hi|lo|hi] x [Whi|Whi|Wlo]^T, fp32 accumulation in TMEM)
-  DCV_TRY(gemm_nt(a.patches, 3 * K, a.wsplit, 3 * K, d.B * T, D, 3 * K, EPI_EMBED, nullptr, a.tokens, nullptr, nullptr,
-                  nullptr, D, false, st, T, T + 1, a.addend));
   const bool tdl_on = cfg.lambda_tdl > 0.f, cdl_on = cfg.lambda_cdl > 0.f;
-  if (tdl_on)
-    DCV_TRY(tdl_fwd(a.tokens, a.addend, p.proj_b, a.S, a.Q, a.rnorm, a.S_all, a.loss_b, a.coef_pos, a.coef_neg, a.tdl,
-                    d.B, d.Cs, N, D, cfg.gamma_s, cfg.gamma_d, cfg.reverse_pos_pairs, cfg.use_square, st));
+  if (fused) {
+    // one kernel: TMA from the fp32 image -> bf16 hi/lo split in shared memory -> tcgen05 -> tokens + the per-(image,
+    // channel) sums of normalised tokens TDL needs (embed_fused.cu)
+    DCV_TRY(embed_fused_fwd(d, x, idx, a.wsplit, p.proj_b, a.addend, a.tokens, a.patches, a.S, a.Q, a.rnorm, tdl_on ? 1 : 0,
+                            st));
+    if (tdl_on)
+      DCV_TRY(tdl_finish(a.S, a.Q, a.S_all, a.loss_b, a.coef_pos, a.coef_neg, a.tdl, d.B, d.Cs, N, D, cfg.gamma_s,
+                         cfg.gamma_d, cfg.reverse_pos_pairs, cfg.use_square, st));
+  } else {
+    DCV_TRY(gemm_nt(a.patches, 3 * K, a.wsplit, 3 * K, d.B * T, D, 3 * K, EPI_EMBED, nullptr, a.tokens, nullptr, nullptr,
+                    nullptr, D, false, st, T, T + 1, a.addend));
+    if (tdl_on)
+      DCV_TRY(tdl_fwd(a.tokens, a.addend, p.proj_b, a.S, a.Q, a.rnorm, a.S_all, a.loss_b, a.coef_pos, a.coef_neg, a.tdl,
+                      d.B, d.Cs, N, D, cfg.gamma_s, cfg.gamma_d, cfg.reverse_pos_pairs, cfg.use_square, st));
+  }
   if (cdl_on) {
     if (!p.proxies) return set_error(DCV_ERR_INVALID, "embed_fwd: CDL on but proxies == NULL");
     DCV_TRY(cdl_fwd(p.chan_embed, p.proxies, gid, cfg.cdl_scale, a.cdl, a.cdl_dE, a.cdl_dP, d.Cs, D, st));

@@ -324,6 +324,10 @@ void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode);
  * (tools/pdl_ab.py): faster only for the shortest sequences, slower from ~800 tokens up -- hence opt-in. */
 void dcv_debug_set_pdl(int on);
 
+/* debug / A-B timing: 0 = always use the three-kernel patch embedding (gather + GEMM + TDL sums) instead of the fused
+ * TMA-fed kernel (default 1 where the shape allows it: P = 16, D = 384, fp32 input; DCV_EMBED_FUSED=0 in the environment) */
+void dcv_debug_set_embed_fused(int on);
+
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);
 
