@@ -418,6 +418,7 @@ int dcv_debug_attn_timeline(long long* buf) { return debug_attn_timeline(buf); }
 
 void dcv_debug_set_pdl(int on) { debug_set_pdl(on); }
 void dcv_debug_set_embed_fused(int on) { debug_set_embed_fused(on); }
+int dcv_debug_embed_timeline(long long* buf) { return debug_embed_timeline(buf); }
 
 void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode) {
   if (fwd_mode >= 0) debug_set_attn_fwd_mode(fwd_mode);

@@ -168,6 +168,7 @@ int cls_ln_bwd(const float* dfeat, const float* x, long long row_stride, const f
 // ---- embed_fused.cu ----
 bool embed_fused_ok(const dcv_embed_dims& d, int x_is_u8);
 void debug_set_embed_fused(int on);
+int debug_embed_timeline(long long* buf);
 int embed_fused_fwd(const dcv_embed_dims& d, const void* x, const int* idx, const void* wsplit, const float* bias,
                     const float* addend, float* tokens, void* patches, float* S, float* Q, float* rnorm, int tdl_on,
                     cudaStream_t st);

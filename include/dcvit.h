@@ -324,9 +324,15 @@ void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode);
  * (tools/pdl_ab.py): faster only for the shortest sequences, slower from ~800 tokens up -- hence opt-in. */
 void dcv_debug_set_pdl(int on);
 
-/* debug / A-B timing: 0 = always use the three-kernel patch embedding (gather + GEMM + TDL sums) instead of the fused
- * TMA-fed kernel (default 1 where the shape allows it: P = 16, D = 384, fp32 input; DCV_EMBED_FUSED=0 in the environment) */
+/* debug / A-B timing of the patch embedding: 0 = the three-kernel path (gather + GEMM + TDL sums), 1 = the fused TMA-fed
+ * kernel with one tile per CTA, 2 = the fused kernel as a persistent, cross-tile pipelined kernel, < 0 = back to the
+ * default (DCV_EMBED_FUSED=0|1|2 in the environment overrides the default).  The fused kernels need P = 16, D = 384 and
+ * fp32 input; other shapes always take the three-kernel path. */
 void dcv_debug_set_embed_fused(int on);
+
+/* debug: when buf != NULL (device memory, >= 128 int64), one CTA of the fused patch-embedding kernel records clock64()
+ * stamps of its pipeline stages into it (tools/embed_timeline.py); NULL switches the recording off */
+int dcv_debug_embed_timeline(long long* buf);
 
 /* debug: override the MN-major shared-memory descriptor strides of dcv_gemm_tn (0 = default) */
 void dcv_debug_set_tn_desc(int lbo_bytes, int sbo_bytes);

@@ -12,15 +12,17 @@ from tests.util import O, build_cuda_model, cases, cuda_step, make_inputs, rel_l
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("indices", [None, [5, 0, 3], [2]])
-def test_fused_patch_embedding_equals_three_kernel_path(indices):
+def test_fused_patch_embedding_equals_three_kernel_path(indices, mode):
+    """mode 1: one tile per CTA; mode 2: the persistent, cross-tile pipelined kernel."""
     oc, mapper, chunk, has_head, B, wseed, iseed, xlam = cases()["full_c3"]
     weights = O.make_weights(oc, has_head, wseed)
     x, y = make_inputs(oc, B, len(mapper[chunk]), oc.num_classes, iseed)
     res = {}
     lib = _lib.lib()
     try:
-        for fused in (1, 0):
+        for fused in (mode, 0):
             lib.dcv_debug_set_embed_fused(fused)
             model = build_cuda_model(oc, mapper, weights)
             out, extra, loss, grads = cuda_step(model, x.cuda(), y.cuda(), chunk, has_head, xlam, indices=indices)
@@ -28,8 +30,8 @@ def test_fused_patch_embedding_equals_three_kernel_path(indices):
             res[fused] = (out.detach().clone(), extra.detach().clone(), {k: v.item() for k, v in model.last_losses.items()},
                           {k: g.detach().clone() for k, g in grads.items() if g is not None})
     finally:
-        lib.dcv_debug_set_embed_fused(1)
-    (o1, e1, l1, g1), (o0, e0, l0, g0) = res[1], res[0]
+        lib.dcv_debug_set_embed_fused(-1)
+    (o1, e1, l1, g1), (o0, e0, l0, g0) = res[mode], res[0]
     # the losses are fp32 reductions of the fp32 projection: only the summation order differs
     assert abs(l1["tdl"] - l0["tdl"]) <= 1e-5 * abs(l0["tdl"]) + 1e-9
     assert abs(l1["cdl"] - l0["cdl"]) <= 1e-6 * abs(l0["cdl"]) + 1e-9

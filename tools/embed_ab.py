@@ -6,7 +6,7 @@ import os
 import subprocess
 import sys
 
-for f in ("0", "1"):
+for f in (sys.argv[1:] or ("0", "1", "2")):
     env = dict(os.environ, DCV_EMBED_FUSED=f)
     out = subprocess.run([sys.executable, "bench.py", "--no-cpu", "--no-eager", "--steps", "10", "--warmup", "3"], env=env,
                          capture_output=True, text=True).stdout.strip().splitlines()[-1]
