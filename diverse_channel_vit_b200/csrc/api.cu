@@ -69,6 +69,49 @@ bool pdl_enabled() {
 }
 void debug_set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
+// ---------------------------------------------------------------------------------------------
+// side stream of the block backward
+// ---------------------------------------------------------------------------------------------
+// 0 = off, 1 = always, n > 1 = only for calls of at most n token rows; < 0 = not read yet (DCV_BWD_OVERLAP)
+constexpr long long kBwdOverlapDefault = 1;
+static std::atomic<long long> g_bwd_overlap{-1};
+void debug_set_bwd_overlap(int on) { g_bwd_overlap.store(on < 0 ? -1 : on, std::memory_order_relaxed); }
+
+SideBranch* side_branch(cudaStream_t main, int rows) {
+  long long mode = g_bwd_overlap.load(std::memory_order_relaxed);
+  if (mode < 0) {
+    const char* e = getenv("DCV_BWD_OVERLAP");
+    mode = (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoll(e) : kBwdOverlapDefault;
+    g_bwd_overlap.store(mode, std::memory_order_relaxed);
+  }
+  if (mode == 0 || (mode > 1 && rows > mode) || g_prof_on.load(std::memory_order_relaxed)) return nullptr;
+  static std::mutex mu;
+  static SideBranch by_dev[64];
+  static bool ready[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!ready[dev]) {
+    // never create a stream while the caller is capturing (global capture mode rejects it): that call stays serial
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    SideBranch sb;
+    if (cudaStreamCreateWithFlags(&sb.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    bool ok = cudaEventCreateWithFlags(&sb.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&sb.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    by_dev[dev] = sb;
+    ready[dev] = true;
+  }
+  return &by_dev[dev];
+}
+
 int num_sms() {
   static std::atomic<int> sms_by_dev[64];
   int dev = 0;
@@ -417,6 +460,7 @@ void dcv_debug_set_nt_cluster(int cm) { debug_set_nt_cluster(cm); }
 int dcv_debug_attn_timeline(long long* buf) { return debug_attn_timeline(buf); }
 
 void dcv_debug_set_pdl(int on) { debug_set_pdl(on); }
+void dcv_debug_set_bwd_overlap(int on) { debug_set_bwd_overlap(on); }
 void dcv_debug_set_embed_fused(int on) { debug_set_embed_fused(on); }
 int dcv_debug_embed_timeline(long long* buf) { return debug_embed_timeline(buf); }
 

@@ -647,7 +647,7 @@ int debug_attn_timeline(long long* buf) {
 
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
              void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only, bool delta_ready,
-             float* dbias_qkv) {
+             float* dbias_qkv, bool dq_cleared) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(DCV_ERR_INVALID, "attn_bwd: empty problem");
   const int D = H * kHd;
   const int Lp = (L + 127) / 128 * 128;
@@ -684,7 +684,7 @@ int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, 
           reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(dO), delta, B, L, H, Lp);
     }
     DCV_CUDA(cudaGetLastError());
-    DCV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * H * L * kHd * sizeof(float), st));
+    if (!dq_cleared) DCV_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * H * L * kHd * sizeof(float), st));
   }
   AttnBwdParams p;
   p.B = B; p.L = L; p.H = H; p.D = D; p.Lp = Lp;

@@ -633,7 +633,7 @@ int debug_embed_timeline(long long* buf) {
   return 0;
 }
 
-constexpr int kEmbedFusedDefault = 1;
+constexpr int kEmbedFusedDefault = 2;
 // 0 = three-kernel path, 1 = one tile per CTA, 2 = persistent pipelined kernel
 static int g_embed_fused = -1;
 void debug_set_embed_fused(int on) { g_embed_fused = on < 0 ? -1 : (on > 2 ? 2 : on); }  // < 0: back to the default

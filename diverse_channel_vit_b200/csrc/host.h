@@ -94,11 +94,12 @@ int attn_fwd(const void* qkv, void* o, float* lse2, int B, int L, int H, float s
 // cls_only: dO is compact [B, D] (gradient of the CLS rows of o, every other row being zero); only query tile 0 is
 // visited, dK / dV / dQ are still produced for all rows
 // dbias_qkv: optional [3D] fp32, the column sums of dqkv (= qkv bias gradient) are ADDED to it
+// dq_cleared: the caller has already zeroed dq_acc (the block backward does it on its side stream)
 // delta_ready: delta[b,h,q] = sum_d dO*O was already produced (epilogue of the projection dgrad GEMM, EPI_DELTA; pad
 // rows [L, Lp) zero); otherwise a prep kernel computes it here
 int attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse2, float* delta, float* dq_acc,
              void* dqkv, int B, int L, int H, float scale, cudaStream_t st, bool cls_only = false,
-             bool delta_ready = false, float* dbias_qkv = nullptr);
+             bool delta_ready = false, float* dbias_qkv = nullptr, bool dq_cleared = false);
 
 int debug_attn_timeline(long long* buf);
 void debug_set_attn_fwd_mode(int m);
@@ -122,6 +123,30 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+
+// ---- side stream (api.cu) ----
+// Work of one launcher call that does not sit on its critical path (the weight-gradient GEMMs and the accumulator
+// clears of the block backward) runs on a per-device side stream, forked from / joined into the caller's stream with
+// events: under stream capture the fork / join become edges of the CUDA graph (a parallel branch), eagerly they are
+// ordinary cross-stream dependencies.  side_branch() returns nullptr -- the caller then keeps everything on its own
+// stream -- when the overlap is switched off (DCV_BWD_OVERLAP=0 / dcv_debug_set_bwd_overlap(0)), while the built-in
+// profiler is recording (its per-class event pairs assume one kernel at a time), and when the stream / events of this
+// device would have to be created while `main` is being captured.
+struct SideBranch {
+  cudaStream_t s;
+  cudaEvent_t fork;
+  cudaEvent_t join[4];
+};
+SideBranch* side_branch(cudaStream_t main, int rows);
+void debug_set_bwd_overlap(int on);
+// side waits for everything enqueued on `main` so far
+inline cudaError_t side_fork(SideBranch* sb, cudaStream_t main) {
+  cudaError_t e = cudaEventRecord(sb->fork, main);
+  return e != cudaSuccess ? e : cudaStreamWaitEvent(sb->s, sb->fork, 0);
+}
+// `main` waits for everything enqueued on the side stream before join mark i was set
+inline cudaError_t side_mark(SideBranch* sb, int i) { return cudaEventRecord(sb->join[i], sb->s); }
+inline cudaError_t side_join(SideBranch* sb, int i, cudaStream_t main) { return cudaStreamWaitEvent(main, sb->join[i], 0); }
 
 // ---- rowops.cu ----
 int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int D,

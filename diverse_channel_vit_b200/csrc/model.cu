@@ -39,34 +39,59 @@ int block_bwd(const dcv_dims& d, const dcv_block_params& p, const dcv_block_acts
               const dcv_block_ws& ws, float* dres, void* dres_bf16, float* dbias_prev, cudaStream_t st) {
   DCV_TRY(check_dims(d));
   const int M = d.B * d.L, D = d.D, F = d.F;
+  // The chain dgrad -> LayerNorm backward -> attention backward -> dgrad is the critical path; the four weight
+  // gradients and the two accumulator clears only have to be complete when their inputs are overwritten (dres_bf16 by
+  // the LayerNorm backward passes) resp. when the block returns.  They go to the side stream (sb != nullptr), w = the
+  // stream they are enqueued on.
+  SideBranch* sb = side_branch(st, M);
+  const cudaStream_t w = sb ? sb->s : st;
+  const size_t delta_bytes = static_cast<size_t>(d.B) * d.H * ((d.L + 127) / 128 * 128) * sizeof(float);
+  const size_t dq_bytes = static_cast<size_t>(d.B) * d.H * d.L * 64 * sizeof(float);
+  if (sb) {
+    DCV_CUDA(side_fork(sb, st));
+    // dW2 += dres^T g                    [D,F]
+    DCV_TRY(gemm_tn(dres_bf16, D, a.g, F, M, D, F, g.fc2_w, F, 1, 0, w));
+    if (d.L % 128) DCV_CUDA(cudaMemsetAsync(ws.delta, 0, delta_bytes, w));
+    DCV_CUDA(cudaMemsetAsync(ws.dq_acc, 0, dq_bytes, w));
+    DCV_CUDA(side_mark(sb, 0));
+  }
   // ---- MLP branch:  x_out = x_mid + fc2(gelu(fc1(LN2 x_mid))) ----
   // dh = (dres W2) o gelu'(h)            [M,F]
   // (the column sums of dh = fc1 bias gradient are accumulated by the same epilogue)
   DCV_TRY(gemm_nt(dres_bf16, D, p.fc2_w, F, M, F, D, EPI_DGELU, nullptr, ws.dh, nullptr, nullptr, a.h, F, true, st, 0, 0,
                   nullptr, 0, g.fc1_b));
-  // dW2 += dres^T g                      [D,F]
-  DCV_TRY(gemm_tn(dres_bf16, D, a.g, F, M, D, F, g.fc2_w, F, 1, 0, st));
+  if (!sb) DCV_TRY(gemm_tn(dres_bf16, D, a.g, F, M, D, F, g.fc2_w, F, 1, 0, st));
   // dv = dh W1                           [M,D]
+  if (sb) DCV_CUDA(side_fork(sb, st));  // dh is complete
   DCV_TRY(gemm_nt(ws.dh, F, p.fc1_w, D, M, D, F, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
   // dW1 += dh^T v
-  DCV_TRY(gemm_tn(ws.dh, F, a.v, D, M, F, D, g.fc1_w, D, 1, 0, st));
-  // dres += LN2'(dv); column sums of the result = d proj bias
+  DCV_TRY(gemm_tn(ws.dh, F, a.v, D, M, F, D, g.fc1_w, D, 1, 0, w));
+  // dres += LN2'(dv); column sums of the result = d proj bias.  Overwrites dres_bf16: dW2 has to be through with it
+  if (sb) DCV_CUDA(side_join(sb, 0, st));
   DCV_TRY(ln_bwd(ws.dv, a.x_mid, a.mean2, a.rstd2, p.ln2_w, dres, dres_bf16, g.ln2_w, g.ln2_b, g.proj_b, M, D, st));
   // ---- attention branch:  x_mid = x_in + proj(attn(qkv(LN1 x_in))) ----
   // dO = dres Wproj, with delta[b,h,q] = sum_d dO*O (the softmax-backward row term) from the same epilogue
-  if (d.L % 128)
-    DCV_CUDA(cudaMemsetAsync(ws.delta, 0, static_cast<size_t>(d.B) * d.H * ((d.L + 127) / 128 * 128) * sizeof(float), st));
+  if (!sb && d.L % 128) DCV_CUDA(cudaMemsetAsync(ws.delta, 0, delta_bytes, st));
+  if (sb) DCV_CUDA(side_fork(sb, st));  // the new dres_bf16 is complete
   DCV_TRY(gemm_nt(dres_bf16, D, p.proj_w, D, M, D, D, EPI_DELTA, nullptr, ws.d_o, nullptr, nullptr, a.o, D, true, st, 0, 0,
                   nullptr, 0, ws.delta, d.L));
-  DCV_TRY(gemm_tn(dres_bf16, D, a.o, D, M, D, D, g.proj_w, D, 1, 0, st));
+  DCV_TRY(gemm_tn(dres_bf16, D, a.o, D, M, D, D, g.proj_w, D, 1, 0, w));
+  if (sb) DCV_CUDA(side_mark(sb, 1));
   // the qkv bias gradient (column sums of dqkv) comes out of the attention-backward epilogues
   float* fused_db = g.qkv_b;
   DCV_TRY(attn_bwd(a.qkv, a.o, ws.d_o, a.lse2, ws.delta, ws.dq_acc, ws.dqkv, d.B, d.L, d.H, 0.125f, st, false, true,
-                   fused_db));
+                   fused_db, sb != nullptr));
+  if (sb) DCV_CUDA(side_fork(sb, st));  // dqkv is complete
   DCV_TRY(gemm_nt(ws.dqkv, 3 * D, p.qkv_w, D, M, D, 3 * D, EPI_BIAS, nullptr, ws.dv, nullptr, nullptr, nullptr, D, true, st));
-  DCV_TRY(gemm_tn(ws.dqkv, 3 * D, a.u, D, M, 3 * D, D, g.qkv_w, D, 1, 0, st));
+  DCV_TRY(gemm_tn(ws.dqkv, 3 * D, a.u, D, M, 3 * D, D, g.qkv_w, D, 1, 0, w));
   if (!fused_db) DCV_TRY(colsum_bf16(ws.dqkv, g.qkv_b, M, 3 * D, 3 * D, st));
+  // overwrites dres_bf16: the projection weight gradient has to be through with it
+  if (sb) DCV_CUDA(side_join(sb, 1, st));
   DCV_TRY(ln_bwd(ws.dv, a.x_in, a.mean1, a.rstd1, p.ln1_w, dres, dres_bf16, g.ln1_w, g.ln1_b, dbias_prev, M, D, st));
+  if (sb) {  // everything of this call is ordered before whatever the caller enqueues next
+    DCV_CUDA(side_mark(sb, 2));
+    DCV_CUDA(side_join(sb, 2, st));
+  }
   return 0;
 }
 

@@ -324,6 +324,12 @@ void dcv_debug_set_attn_mode(int fwd_mode, int bwd_mode);
  * (tools/pdl_ab.py): faster only for the shortest sequences, slower from ~800 tokens up -- hence opt-in. */
 void dcv_debug_set_pdl(int on);
 
+/* debug / A-B timing: the block backward runs its weight-gradient GEMMs and accumulator clears on a side stream of the
+ * library (a parallel branch of the graph when the call is captured), joined back before dcv_block_bwd returns to the
+ * caller's stream.  0 = everything on the caller's stream, 1 = always, n > 1 = only for calls of at most n token rows,
+ * < 0 = back to the default (DCV_BWD_OVERLAP in the environment overrides the default). */
+void dcv_debug_set_bwd_overlap(int on);
+
 /* debug / A-B timing of the patch embedding: 0 = the three-kernel path (gather + GEMM + TDL sums), 1 = the fused TMA-fed
  * kernel with one tile per CTA, 2 = the fused kernel as a persistent, cross-tile pipelined kernel, < 0 = back to the
  * default (DCV_EMBED_FUSED=0|1|2 in the environment overrides the default).  The fused kernels need P = 16, D = 384 and
