@@ -10,8 +10,14 @@
  * Conventions
  *   - plain pointers and sizes only; all pointers are DEVICE pointers.  The caller
  *     owns every buffer, including activations kept for backward and workspaces.
- *   - `stream` is a cudaStream_t passed as void*.  Functions only enqueue work:
- *     no allocation, no synchronisation, no global mutable state.
+ *   - `stream` is a cudaStream_t passed as void*.  Functions only enqueue work: no device
+ *     allocation, no synchronisation.  Process-wide state is limited to caches and switches that
+ *     do not change results: per-(kernel, device) shared-memory opt-ins, a per-thread cache of
+ *     encoded TMA descriptors, the launch counter / profiler, the dcv_debug_* A/B switches, and
+ *     one side stream + a few events per device (dcv_block_bwd forks its weight-gradient GEMMs
+ *     onto it and joins them back into `stream` before it returns, so from the caller's point of
+ *     view everything is still ordered on `stream`; under stream capture the fork / join become
+ *     graph edges).
  *   - return 0 on success, a negative DCV_ERR_* otherwise; dcv_last_error()
  *     returns a thread-local message for the last failure.
  *   - bf16 buffers are void*, fp32 are float*.  "[r, c]" is row-major.
