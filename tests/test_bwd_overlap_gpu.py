@@ -32,6 +32,7 @@ def _grads(overlap, case, reps=1):
 @pytest.mark.parametrize("case", ["tiny_jumpcp", "full_c3"])
 def test_side_branch_backward_equals_serial_backward(case):
     o0, g0 = _grads(0, case)
+    _, g0b = _grads(0, case)         # the serial backward against itself: the run-to-run noise floor
     o1, g1 = _grads(1, case, reps=3)  # repeated: a race would not hit the same way three times in a row
     assert rel_l2(o1, o0) < 1e-6  # the forward is untouched
     assert set(g0) == set(g1)
@@ -39,8 +40,13 @@ def test_side_branch_backward_equals_serial_backward(case):
         if g0[k].abs().max() == 0:
             assert g1[k].abs().max() == 0, k
             continue
-        # same kernels on the same data: only the order of the fp32 reduce-adds / atomics differs
-        assert rel_l2(g1[k], g0[k]) < 2e-3, k
+        # Same kernels on the same data: only the order of the fp32 reduce-adds / atomics differs, exactly as between two
+        # serial runs -- but a last-bit difference in a bf16 rounding of dqkv propagates through up to 12 blocks, so the
+        # bound is relative to what two serial runs differ by (measured at the full size: 5e-3 on cls_token, ~1e-3 on
+        # the weight matrices).  A missing fork / join edge (a weight gradient computed from a half-overwritten
+        # dres_bf16 / dh / dqkv) is an O(0.1 - 1) error on that block's weights.
+        noise = rel_l2(g0b[k], g0[k])
+        assert rel_l2(g1[k], g0[k]) < max(4 * noise, 2e-3), (k, noise)
 
 
 def test_row_threshold_keeps_large_calls_serial():
