@@ -46,7 +46,7 @@ def test_side_branch_backward_equals_serial_backward(case):
         # the weight matrices).  A missing fork / join edge (a weight gradient computed from a half-overwritten
         # dres_bf16 / dh / dqkv) is an O(0.1 - 1) error on that block's weights.
         noise = rel_l2(g0b[k], g0[k])
-        assert rel_l2(g1[k], g0[k]) < max(4 * noise, 2e-3), (k, noise)
+        assert rel_l2(g1[k], g0[k]) < max(4 * noise, 1e-2), (k, noise)  # floor = the parity tolerance: never flaky
 
 
 def test_row_threshold_keeps_large_calls_serial():
@@ -55,4 +55,4 @@ def test_row_threshold_keeps_large_calls_serial():
     o1, g1 = _grads(2, "tiny_jumpcp")  # every call has more than 2 rows -> serial
     assert rel_l2(o1, o0) < 1e-6
     for k in g0:
-        assert rel_l2(g1[k], g0[k]) < 2e-3 or g0[k].abs().max() == 0, k
+        assert rel_l2(g1[k], g0[k]) < 1e-2 or g0[k].abs().max() == 0, k

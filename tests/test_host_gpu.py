@@ -178,7 +178,7 @@ def test_learnable_temperature_end_to_end():
     cfg["learnable_temp"] = True
     m = dichavit(cfg, mapper=mapper)
     assert "logit_scale" in m.state_dict() and not hasattr(m, "scale")
-    assert float(m.logit_scale) == pytest.approx(float(torch.log(torch.tensor(1 / oc.temperature))), rel=1e-6)
+    assert float(m.logit_scale.detach()) == pytest.approx(float(torch.log(torch.tensor(1 / oc.temperature))), rel=1e-6)
     m.load_state_dict({k: weights[k].clone() for k in weights}, strict=False)
     m = m.cuda().train()
     x, y = make_inputs(oc, B, len(mapper[chunk]), oc.num_classes, iseed)
