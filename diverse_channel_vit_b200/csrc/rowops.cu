@@ -16,7 +16,7 @@ constexpr int kRowWarps = 8;  // warps per CTA
 // LayerNorm forward: x fp32 [M,D] -> y bf16 [M,D], mean/rstd fp32 [M]
 // ---------------------------------------------------------------------------------
 template <int NV>  // float4 per lane, NV = ceil(D / 128)
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, NV <= 3 ? 4 : 2)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int M, int D,
               float eps) {
@@ -37,15 +37,31 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
     }
   }
   const float inv_d = 1.0f / static_cast<float>(D);
-  for (int row = blockIdx.x * kRowWarps + warp; row < M; row += gridDim.x * kRowWarps) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  // Software pipeline: the next row's loads are in flight while this row goes through its two dependent warp
+  // reductions and its stores (the un-pipelined loop left a warp with nothing outstanding for ~2/3 of a row's time:
+  // 0.71 of the HBM copy bandwidth against 0.87 for the pipelined backward kernel).
+  const int stride = gridDim.x * kRowWarps;
+  int row = blockIdx.x * kRowWarps + warp;
+  float4 nx[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int idx = lane + 32 * k;
+    nx[k] = (row < M && idx < nvec) ? reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D)[idx]
+                                    : make_float4(0, 0, 0, 0);
+  }
+  for (; row < M; row += stride) {
     float4 v[NV];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int idx = lane + 32 * k;
-      v[k] = idx < nvec ? xr[idx] : make_float4(0, 0, 0, 0);
+      v[k] = nx[k];
       s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const int next = row + stride;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = lane + 32 * k;
+      if (next < M && idx < nvec) nx[k] = reinterpret_cast<const float4*>(x + static_cast<size_t>(next) * D)[idx];
     }
     const float mu = warp_sum(s) * inv_d;
     float q = 0.f;
@@ -426,7 +442,9 @@ int ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float
   if (M <= 0 || D <= 0) return set_error(DCV_ERR_INVALID, "ln_fwd: empty problem");
   if (D % 4) return set_error(DCV_ERR_UNSUPPORTED, "ln_fwd: D=%d must be a multiple of 4", D);
   ProfScope prof(PT_LN_FWD, st);
-  const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * 8);
+  // one resident wave: 4 CTAs of 8 warps per SM (<= 64 registers; 2 CTAs for D = 768, whose rows need twice the
+  // registers), every warp walks its rows with a one-row prefetch
+  const int blocks = min((M + kRowWarps - 1) / kRowWarps, num_sms() * (nv_for(D) <= 3 ? 4 : 2));
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   switch (nv_for(D)) {
     case 1: DCV_CUDA(launch_pdl(ln_fwd_kernel<1>, dim3(blocks), dim3(kRowWarps * 32), 0, st, x, gamma, beta, yb, mean, rstd, M, D, eps)); break;
