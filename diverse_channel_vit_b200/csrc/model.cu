@@ -203,6 +203,12 @@ int embed_bwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed
   if (!G || !gid || !ws.dY || !ws.R) return set_error(DCV_ERR_INVALID, "embed_bwd: null pointer");
   const int N = (d.H / d.P) * (d.W / d.P), T = d.Cs * N, K = d.P * d.P, D = d.D, M = d.B * T;
   const bool tdl_on = cfg.lambda_tdl > 0.f && d_extra != nullptr, cdl_on = cfg.lambda_cdl > 0.f && d_extra != nullptr;
+  // Two independent chains off the token gradient G: (1) dY -> conv weight / bias gradients, (2) batch sum -> cls / pos /
+  // channel-token gradients (-> CDL's share of the channel-token gradient, same buffers, same stream).  Chain (2) is
+  // five short latency-bound launches: it goes to the side stream (see side_branch() in host.h) when there is one.
+  SideBranch* sb = side_branch(st, M);
+  const cudaStream_t w = sb ? sb->s : st;
+  if (sb) DCV_CUDA(side_fork(sb, st));
   // dY = G[:, 1:] + lambda_tdl * d_extra * dTDL/dY   (Appendix C of SURVEY.md)
   DCV_TRY(embed_bwd_dy(G, a.tokens, a.addend, p.proj_b, a.rnorm, tdl_on ? a.S : nullptr, a.S_all, a.coef_pos, a.coef_neg,
                        d_extra, tdl_on ? cfg.lambda_tdl : 0.f, ws.dY, d.B, d.Cs, N, D, st));
@@ -211,10 +217,14 @@ int embed_bwd(const dcv_embed_dims& d, const dcv_embed_cfg& cfg, const dcv_embed
   DCV_TRY(colsum_bf16(ws.dY, g.proj_b, M, D, D, st));
   // cls / pos / channel-token gradients from the batch-summed token gradient
   float* pos_patch_grad = p.pos_map ? ws.dpos_patch : g.pos + D;
-  DCV_TRY(embed_param_grads(G, ws.R, gid, g.cls, g.pos, g.chan_embed, pos_patch_grad, p.pos_map ? 0 : 1, d.B, d.Cs, N, D, st));
+  DCV_TRY(embed_param_grads(G, ws.R, gid, g.cls, g.pos, g.chan_embed, pos_patch_grad, p.pos_map ? 0 : 1, d.B, d.Cs, N, D, w));
   if (p.pos_map)  // d pos[1:] += pos_map^T dpos_patch
-    DCV_TRY(sgemm_small(p.pos_map, N, 1, ws.dpos_patch, D, 0, g.pos + D, D, nullptr, 1, N, D, N, st));
-  if (cdl_on) DCV_TRY(cdl_bwd(a.cdl_dE, a.cdl_dP, gid, d_extra, cfg.lambda_cdl, g.chan_embed, g.proxies, d.Cs, D, st));
+    DCV_TRY(sgemm_small(p.pos_map, N, 1, ws.dpos_patch, D, 0, g.pos + D, D, nullptr, 1, N, D, N, w));
+  if (cdl_on) DCV_TRY(cdl_bwd(a.cdl_dE, a.cdl_dP, gid, d_extra, cfg.lambda_cdl, g.chan_embed, g.proxies, d.Cs, D, w));
+  if (sb) {
+    DCV_CUDA(side_mark(sb, 0));
+    DCV_CUDA(side_join(sb, 0, st));
+  }
   return 0;
 }
 
@@ -238,17 +248,23 @@ int head_bwd(const float* d_out, const float* x_last, int B, int L, int D, const
              void* dres_bf16, float* g_norm_w, float* g_norm_b, float* g_head_w, float* g_head_b, float* dbias_last,
              cudaStream_t st) {
   if (!d_out || !x_last || !dres || !dres_bf16) return set_error(DCV_ERR_INVALID, "head_bwd: null pointer");
+  if (head_w && !dfeat_ws) return set_error(DCV_ERR_INVALID, "head_bwd: dfeat workspace missing");
   const size_t n = static_cast<size_t>(B) * L * D;
-  DCV_CUDA(cudaMemsetAsync(dres, 0, n * sizeof(float), st));
-  DCV_CUDA(cudaMemsetAsync(dres_bf16, 0, n * 2, st));
+  // the two full-size clears run beside the head's small GEMMs (side stream), joined before the CLS rows are written
+  SideBranch* sb = side_branch(st, B * L);
+  const cudaStream_t w = sb ? sb->s : st;
+  if (sb) DCV_CUDA(side_fork(sb, st));
+  DCV_CUDA(cudaMemsetAsync(dres, 0, n * sizeof(float), w));
+  DCV_CUDA(cudaMemsetAsync(dres_bf16, 0, n * 2, w));
+  if (sb) DCV_CUDA(side_mark(sb, 0));
   const float* dfeat = d_out;
   if (head_w) {
-    if (!dfeat_ws) return set_error(DCV_ERR_INVALID, "head_bwd: dfeat workspace missing");
     DCV_TRY(sgemm_small(d_out, num_classes, 0, head_w, D, 0, dfeat_ws, D, nullptr, 0, B, D, num_classes, st));
     if (g_head_w) DCV_TRY(sgemm_small(d_out, num_classes, 1, feat, D, 0, g_head_w, D, nullptr, 1, num_classes, D, B, st));
     if (g_head_b) DCV_TRY(colsum_f32(d_out, g_head_b, B, num_classes, num_classes, st));
     dfeat = dfeat_ws;
   }
+  if (sb) DCV_CUDA(side_join(sb, 0, st));
   DCV_TRY(cls_ln_bwd(dfeat, x_last, static_cast<long long>(L) * D, mean, rstd, norm_w, dres, dres_bf16, g_norm_w, g_norm_b,
                      dbias_last, B, D, st));
   return 0;

@@ -14,10 +14,10 @@
  *     allocation, no synchronisation.  Process-wide state is limited to caches and switches that
  *     do not change results: per-(kernel, device) shared-memory opt-ins, a per-thread cache of
  *     encoded TMA descriptors, the launch counter / profiler, the dcv_debug_* A/B switches, and
- *     one side stream + a few events per device (dcv_block_bwd forks its weight-gradient GEMMs
- *     onto it and joins them back into `stream` before it returns, so from the caller's point of
- *     view everything is still ordered on `stream`; under stream capture the fork / join become
- *     graph edges).
+ *     one side stream + a few events per device (dcv_block_bwd / dcv_embed_bwd / dcv_head_bwd fork
+ *     work that is off their critical path onto it and join it back into `stream` before they
+ *     return, so from the caller's point of view everything is still ordered on `stream`; under
+ *     stream capture the fork / join become graph edges; one host thread per device).
  *   - return 0 on success, a negative DCV_ERR_* otherwise; dcv_last_error()
  *     returns a thread-local message for the last failure.
  *   - bf16 buffers are void*, fp32 are float*.  "[r, c]" is row-major.
@@ -332,7 +332,8 @@ void dcv_debug_set_pdl(int on);
 
 /* debug / A-B timing: the block backward runs its weight-gradient GEMMs and accumulator clears on a side stream of the
  * library (a parallel branch of the graph when the call is captured), joined back before dcv_block_bwd returns to the
- * caller's stream.  0 = everything on the caller's stream, 1 = always, n > 1 = only for calls of at most n token rows,
+ * caller's stream; dcv_embed_bwd does the same with its cls / pos / channel-token gradient chain and dcv_head_bwd with
+ * its two full-size clears.  0 = everything on the caller's stream, 1 = always, n > 1 = only for calls of at most n token rows,
  * < 0 = back to the default (DCV_BWD_OVERLAP in the environment overrides the default). */
 void dcv_debug_set_bwd_overlap(int on);
 
