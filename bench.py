@@ -131,6 +131,44 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the CPU (reference) path: oracle restatement of the reference, torch fp32, all host threads
 # ------------------------------------------------------------------------------------------------
+def hbm_kernel_table(prof, subs, depth, D, patch, hbm_peak):
+    """Memory-bound kernel classes: algorithmic bytes per STEP / summed CUDA-event time, against the
+    measured HBM copy bandwidth.  `prof`: {tag: {"ms_per_step", "launches_per_step"}} of the built-in profiler for one
+    full-channel step; `subs`: [(images, tokens per image)] of the step's sub-batches.  Full-size calls only are counted
+    (the last block's CLS-row calls move KBs).  When the one-kernel patch embedding ran (no `im2col` launches) the row
+    `embed_fused` replaces `im2col` + the embedding GEMM + the TDL token pass: fp32 image in, fp32 tokens + the bf16
+    hi-patches (operand of the conv weight gradient) out; the `tdl` tag then only holds two KB-sized follow-up launches
+    and is reported in us, not as a bandwidth."""
+    by = {k: 0.0 for k in ("ln_fwd", "ln_bwd", "colsum", "attn_bwd_fin", "im2col", "tdl", "embed_bwd", "embed_fused")}
+    for nb, Lc in subs:
+        M = nb * Lc
+        Tc = Lc - 1
+        by["ln_fwd"] += (2 * (depth - 1) + 1) * M * D * (4 + 2)
+        by["ln_bwd"] += (2 * (depth - 1) + 1) * M * D * 16
+        by["colsum"] += nb * Tc * D * 2  # patch-embed bias gradient only: the block bias gradients come out of GEMM / attention epilogues
+        by["attn_bwd_fin"] += depth * M * D * (4 + 2)
+        by["im2col"] += nb * Tc * (patch ** 2) * (4 + 6)
+        by["tdl"] += nb * Tc * D * 4
+        by["embed_bwd"] += nb * (2 * Lc * D * 4 + Tc * D * 2) + nb * Lc * D * 4  # dY pass + batch sum of the token gradient
+        by["embed_fused"] += nb * Tc * ((patch ** 2) * (4 + 2) + D * 4)
+    fused = "embed_gemm" in prof and not prof.get("im2col", {}).get("ms_per_step", 0.0)
+    src = {"embed_fused": "embed_gemm"}
+    out = {}
+    for k, nbytes in by.items():
+        if k == "embed_fused" and not fused:
+            continue
+        if fused and k in ("im2col", "tdl"):
+            continue
+        pk = src.get(k, k)
+        if pk in prof and prof[pk]["ms_per_step"] > 0:
+            gbs = nbytes / (prof[pk]["ms_per_step"] * 1e-3) / 1e9
+            out[k] = {"GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 3),
+                      "ms_per_step": round(prof[pk]["ms_per_step"], 4)}
+    if fused and "tdl" in prof:
+        out["tdl_followup"] = {"us_per_step": round(prof["tdl"]["ms_per_step"] * 1e3, 1), "bound": "latency (two KB-sized launches)"}
+    return out
+
+
 def cpu_reference_run(wname: str, steps: int, warmup: int, batch: int, seed: int = 2025):
     """Times fwd+loss+bwd(+AdamW) of the reference algorithm on the host.  Returns (img/s, seconds, cores, sample)."""
     import torch
@@ -526,23 +564,7 @@ def ours(args, wname):
     # memory-bound kernel classes: algorithmic bytes per STEP / summed CUDA-event time, against the
     # measured HBM copy bandwidth.  Full-size calls only are counted (the last block's CLS-row calls move KBs).
     hbm_peak = float(peaks.get("hbm_gbs", 6550.0))
-    by = {k: 0.0 for k in ("ln_fwd", "ln_bwd", "colsum", "attn_bwd_fin", "im2col", "tdl", "embed_bwd")}
-    for nb, Lc in subs:
-        M = nb * Lc
-        Tc = Lc - 1
-        by["ln_fwd"] += (2 * (depth - 1) + 1) * M * D * (4 + 2)
-        by["ln_bwd"] += (2 * (depth - 1) + 1) * M * D * 16
-        by["colsum"] += nb * Tc * D * 2  # patch-embed bias gradient only: the block bias gradients come out of GEMM / attention epilogues
-        by["attn_bwd_fin"] += depth * M * D * (4 + 2)
-        by["im2col"] += nb * Tc * (w["patch"] ** 2) * (4 + 6)
-        by["tdl"] += nb * Tc * D * 4
-        by["embed_bwd"] += nb * (2 * Lc * D * 4 + Tc * D * 2) + nb * Lc * D * 4  # dY pass + batch sum of the token gradient
-    hbm_kernels = {}
-    for k, nbytes in by.items():
-        if k in prof and prof[k]["ms_per_step"] > 0:
-            gbs = nbytes / (prof[k]["ms_per_step"] * 1e-3) / 1e9
-            hbm_kernels[k] = {"GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 3),
-                              "ms_per_step": round(prof[k]["ms_per_step"], 4)}
+    hbm_kernels = hbm_kernel_table(prof, subs, depth, D, w["patch"], hbm_peak)
     attn_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("attn_fwd", "attn_bwd", "attn_bwd_prep", "attn_bwd_fin"))
     attn_tf = (fl["attn_fwd"] + fl["attn_bwd"]) / (attn_ms * 1e-3) / 1e12 if attn_ms else None
     gemm_ms = sum(prof.get(k, {}).get("ms_per_step", 0.0) for k in ("gemm_nt", "gemm_nn", "gemm_tn"))

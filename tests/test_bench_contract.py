@@ -41,3 +41,29 @@ def test_product_arm_needs_cuda():
     r = _run("--steps", "1", "--warmup", "1", "--no-cpu", "--no-eager", timeout=300)
     assert r.returncode != 0  # no CPU fallback: it raises
     assert not any(l.startswith("{") and '"value"' in l for l in r.stdout.splitlines())
+
+
+def test_hbm_kernel_table_reports_the_fused_patch_embedding():
+    """post-processing of the profiler's per-class times into achieved GB/s (pure host code): with the one-kernel patch
+    embedding the row `embed_fused` replaces `im2col` / `tdl`, whose passes over HBM no longer exist"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    rec = json.loads((ROOT / "profiles" / "r2_bench_n1_jumpcp.json").read_text().strip().splitlines()[-1])
+    prof = {k: {"ms_per_step": v, "launches_per_step": 1.0} for k, v in rec["kernel_breakdown_ms_per_step"].items()}
+    assert "im2col" not in prof  # the record was taken on the fused path
+    t = bench.hbm_kernel_table(prof, [(32, 1569)], 12, 384, 16, 6549.0)
+    for k in ("ln_fwd", "ln_bwd", "colsum", "attn_bwd_fin", "embed_bwd"):  # unchanged rows reproduce the record
+        assert abs(t[k]["GB/s"] - rec["hbm_kernels"][k]["GB/s"]) < 0.01 * rec["hbm_kernels"][k]["GB/s"], k
+    assert "im2col" not in t and "tdl" not in t and t["tdl_followup"]["us_per_step"] > 0
+    # 32 x 1568 tokens x (256 px x (4 B read + 2 B hi-patch) + 384 x 4 B token) = 154 MB over the kernel's time
+    ef = t["embed_fused"]
+    assert abs(ef["GB/s"] - 154.14e6 / (prof["embed_gemm"]["ms_per_step"] * 1e-3) / 1e9) < 1.0
+    assert 0.0 < ef["frac_of_hbm_peak"] < 1.0
+    # three-kernel path (ViT-B, So2Sat, uint8 input): the old rows, no fused row
+    prof3 = dict(prof, im2col={"ms_per_step": 0.03, "launches_per_step": 1.0})
+    t3 = bench.hbm_kernel_table(prof3, [(32, 1569)], 12, 384, 16, 6549.0)
+    assert "im2col" in t3 and "tdl" in t3 and "embed_fused" not in t3 and "tdl_followup" not in t3
+    # CHAMMI-style step: several sub-batches with different token counts add up
+    t2 = bench.hbm_kernel_table(prof, [(22, 589), (21, 785), (21, 981)], 12, 384, 16, 6549.0)
+    assert t2["ln_fwd"]["GB/s"] > 0
